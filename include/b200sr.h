@@ -1,0 +1,102 @@
+/*
+ * b200sr.h -- C ABI of the B200-native Real-ESRGAN upscaling engine (libb200sr.so).
+ *
+ * The reference (FrameWright) has no FFI on this path: its upscale processor is Python that
+ * constructs and calls third-party PyTorch code.  Each entry point below therefore cites the
+ * reference *Python* interface whose work it replaces (paths relative to
+ * /root/reference/src/framewright/).  The Python host layer (package `framewright_b200`)
+ * binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions: plain C, no exceptions, no torch types.  Every function returns a status
+ * code (B200SR_OK == 0); b200sr_last_error() gives the message.  One engine per (GPU,
+ * stream); an engine is not thread-safe (callers serialise or use one engine per thread).
+ * Frames are uint8 HWC, BGR channel order (what cv2.imread yields, pytorch_realesrgan.py:198).
+ */
+#ifndef B200SR_H_
+#define B200SR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SR_OK 0
+#define B200SR_ERR_INVALID 1   /* bad argument / unsupported geometry */
+#define B200SR_ERR_CUDA 2      /* CUDA runtime or driver error */
+#define B200SR_ERR_OOM 3       /* device allocation failed -> host layer reports "GPU out of memory" */
+#define B200SR_ERR_STATE 4     /* weights not finalised, etc. */
+
+#define B200SR_ARCH_RRDB 0     /* basicsr RRDBNet   (processors/pytorch_realesrgan.py:107,112,117) */
+#define B200SR_ARCH_SRVGG 1    /* realesrgan SRVGGNetCompact (BASELINE.json north_star) */
+
+typedef struct b200sr_engine b200sr_engine;
+
+/* Architecture descriptor == the RRDBNet(...)/SRVGGNetCompact(...) constructor arguments the
+ * reference passes at processors/pytorch_realesrgan.py:103-129 and cli.py:715-723. */
+typedef struct b200sr_model_desc {
+  int arch;        /* B200SR_ARCH_* */
+  int scale;       /* network scale: 4, or 2 (RRDBNet with pixel-unshuffle input) */
+  int num_feat;    /* 64 */
+  int num_block;   /* RRDB blocks (23 / 6) or SRVGG body convs (32 / 16) */
+  int num_grow_ch; /* 32 */
+} b200sr_model_desc;
+
+/* Replaces: model construction + `.to(device)` inside RealESRGANer.__init__
+ * (called at processors/pytorch_realesrgan.py:160-170). */
+int b200sr_create(const b200sr_model_desc* desc, int device, b200sr_engine** out);
+void b200sr_destroy(b200sr_engine* e);
+
+/* Number of 3x3 conv layers (execution order: processors/... RRDBNet.forward order, see
+ * framewright_b200/archs.py::conv_layers) and of PReLU layers. */
+int b200sr_num_convs(const b200sr_engine* e);
+int b200sr_num_prelus(const b200sr_engine* e);
+
+/* Replaces: `load_state_dict(strict=True)` + `.half()` in RealESRGANer.__init__.
+ * weight: fp32 [cout][cin][3][3] (PyTorch OIHW), bias: fp32 [cout]; host pointers. */
+int b200sr_set_conv(b200sr_engine* e, int layer, const float* weight, const float* bias, int cout, int cin);
+int b200sr_set_prelu(b200sr_engine* e, int index, const float* slope, int n);
+/* Packs weights to the tensor-core layout (bf16, K-major, 128B-swizzled tiles) and uploads. */
+int b200sr_finalize(b200sr_engine* e);
+
+/* Output geometry of `enhance` at the network's native scale. */
+int b200sr_output_dims(const b200sr_engine* e, int h, int w, int* out_h, int* out_w);
+
+/* Device bytes the engine holds for n frames of h x w (tile > 0: per-tile buffers). */
+int b200sr_workspace_bytes(b200sr_engine* e, int n, int h, int w, int tile, int tile_pad, int pre_pad, size_t* bytes);
+
+/* Replaces: RealESRGANer.pre_process / tile_process / process / post_process and the uint8
+ * conversion at the end of RealESRGANer.enhance (called at processors/pytorch_realesrgan.py:223,
+ * processors/enhancement/super_resolution.py:524, cli.py:769), for the 3-channel uint8 branch:
+ *   src: device pointer, n frames [h][w][3] u8 BGR; dst: device pointer, n frames
+ *   [h*scale][w*scale][3] u8 BGR.  tile == 0 -> whole frame; tile > 0 -> upstream tile loop
+ *   (tile, tile_pad) with zero padding at each padded tile's border (seam-exact).
+ *   pre_pad: reflect pad right/bottom before, cropped after.  Asynchronous on `cuda_stream`. */
+int b200sr_enqueue_u8(b200sr_engine* e, const uint8_t* src_dev, uint8_t* dst_dev, int n, int h, int w, int tile,
+                      int tile_pad, int pre_pad, void* cuda_stream);
+
+/* Same with HOST buffers: H2D copy, run, D2H copy, stream sync (the end-to-end call). */
+int b200sr_upscale_host_u8(b200sr_engine* e, const uint8_t* src_host, uint8_t* dst_host, int n, int h, int w,
+                           int tile, int tile_pad, int pre_pad);
+
+/* Number of kernels the last enqueue launched (bench.py reports it as gpu_launches). */
+int b200sr_last_launch_count(const b200sr_engine* e);
+
+/* Debug / measurement hooks (not part of the reference surface). */
+int b200sr_set_option(b200sr_engine* e, const char* key, int value);
+
+/* Test hook: one tensor-core 3x3 conv layer on caller-provided device tensors (bf16 NHWC in/out,
+ * fp32 OIHW host weights).  epi 0: leaky(slope) ; epi 1: PReLU(prelu_host[64]).  Synchronous. */
+int b200sr_debug_conv3x3(int device, const void* in_dev, int n, int h, int w, int in_pitch, int cin,
+                         const float* weight, const float* bias, int cout, int epi, float slope,
+                         const float* prelu_host, void* out_dev, int out_pitch, int out_choff, int force_th,
+                         int max_ctas, void* cuda_stream, char* errbuf, int errbuf_len);
+
+const char* b200sr_last_error(const b200sr_engine* e);
+const char* b200sr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SR_H_ */

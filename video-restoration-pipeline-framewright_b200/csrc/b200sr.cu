@@ -1,0 +1,786 @@
+// libb200sr.so -- engine + C ABI (include/b200sr.h).
+// Host-side walker of the RRDBNet / SRVGGNetCompact forward graphs over the sm_100a kernels in
+// conv3x3_tc.cuh / pointwise.cuh, plus the RealESRGANer pre/post/tile logic
+// (reference call site: /root/reference/src/framewright/processors/pytorch_realesrgan.py:160-170, 223).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/b200sr.h"
+#include "conv3x3_tc.cuh"
+#include "pointwise.cuh"
+#include "tmap.h"
+
+using namespace b200sr;
+
+namespace {
+
+struct Layer {
+  int cin = 0, cout = 0;   // true channel counts
+  int coutp = 0;           // tensor-core N (16 / 32 / 48 / 64)
+  bool set = false;
+  std::vector<float> w, b;      // host fp32 OIHW / bias
+  uint8_t* d_wpack = nullptr;   // packed bf16 image (tensor-core layers)
+  float* d_wfirst = nullptr;    // [9][cin][64] fp32 (first layer, CUDA-core kernel)
+  float* d_bias = nullptr;      // coutp floats
+};
+
+struct Buf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+inline uint16_t f2bf(float f) {  // round-to-nearest-even, matches __float2bfloat16_rn for finite values
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+}  // namespace
+
+struct b200sr_engine {
+  b200sr_model_desc desc{};
+  int device = 0;
+  int num_sms = 148;
+  std::vector<Layer> layers;
+  std::vector<std::vector<float>> prelu_host;
+  std::vector<float*> prelu_dev;
+  bool finalized = false;
+  std::string err;
+  // workspace (grow-only)
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0;
+  // staging for the host-buffer entry point
+  uint8_t* stage_in = nullptr;
+  uint8_t* stage_out = nullptr;
+  size_t stage_in_bytes = 0, stage_out_bytes = 0;
+  cudaStream_t own_stream = nullptr;
+  int launches = 0;
+  int opt_force_th = 0;     // 0 = auto
+  int opt_max_ctas = 0;     // 0 = one per SM
+  bool attrs_set = false;
+};
+
+namespace {
+
+int fail(b200sr_engine* e, int code, const std::string& msg) {
+  if (e) e->err = msg;
+  return code;
+}
+
+#define CUDA_TRY(e, expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t err__ = (expr);                                                                    \
+    if (err__ != cudaSuccess) {                                                                    \
+      int code__ = (err__ == cudaErrorMemoryAllocation) ? B200SR_ERR_OOM : B200SR_ERR_CUDA;        \
+      return fail(e, code__, std::string(#expr) + ": " + cudaGetErrorString(err__));               \
+    }                                                                                              \
+  } while (0)
+
+int coutp_for(int cout) {
+  if (cout <= 16) return 16;
+  if (cout <= 32) return 32;
+  if (cout <= 48) return 48;
+  return 64;
+}
+
+// ---- architecture tables (execution order == framewright_b200/archs.py::conv_layers) ----
+void build_layers(b200sr_engine* e) {
+  const auto& d = e->desc;
+  const int nf = d.num_feat, gc = d.num_grow_ch;
+  auto add = [&](int cin, int cout) {
+    Layer l;
+    l.cin = cin;
+    l.cout = cout;
+    l.coutp = coutp_for(cout);
+    e->layers.push_back(std::move(l));
+  };
+  if (d.arch == B200SR_ARCH_RRDB) {
+    add(d.scale == 2 ? 12 : 3, nf);
+    for (int b = 0; b < d.num_block; ++b)
+      for (int r = 0; r < 3; ++r) {
+        for (int k = 0; k < 4; ++k) add(nf + k * gc, gc);
+        add(nf + 4 * gc, nf);
+      }
+    add(nf, nf);  // conv_body
+    add(nf, nf);  // conv_up1
+    add(nf, nf);  // conv_up2
+    add(nf, nf);  // conv_hr
+    add(nf, 3);   // conv_last
+  } else {
+    add(3, nf);
+    for (int i = 0; i < d.num_block; ++i) add(nf, nf);
+    add(nf, 3 * d.scale * d.scale);
+    e->prelu_host.resize(d.num_block + 1);
+    e->prelu_dev.assign(d.num_block + 1, nullptr);
+  }
+}
+
+// Packed tensor-core weight image: [chunk][dx][blk*COUTP + co][64 ch], 128-byte rows, SWIZZLE_128B,
+// blk 0/1/2 <-> ky 2/1/0 (input row y feeds output rows y-1, y, y+1), dx <-> kx.
+std::vector<uint8_t> pack_weights(const Layer& l) {
+  const int nchunks = (l.cin + 63) / 64;
+  const int COUTP = l.coutp;
+  const size_t tile_bytes = static_cast<size_t>(3) * COUTP * 128;
+  std::vector<uint8_t> img(static_cast<size_t>(nchunks) * 3 * tile_bytes, 0);
+  for (int c = 0; c < nchunks; ++c)
+    for (int dx = 0; dx < 3; ++dx) {
+      uint8_t* tile = img.data() + (static_cast<size_t>(c) * 3 + dx) * tile_bytes;
+      for (int blk = 0; blk < 3; ++blk) {
+        const int ky = 2 - blk;
+        for (int co = 0; co < l.cout; ++co) {
+          const int r = blk * COUTP + co;
+          for (int j = 0; j < 64; ++j) {
+            const int ci = c * 64 + j;
+            if (ci >= l.cin) break;
+            const float v = l.w[((static_cast<size_t>(co) * l.cin + ci) * 3 + ky) * 3 + dx];
+            uint32_t off = static_cast<uint32_t>(r) * 128 + (j / 8) * 16 + (j % 8) * 2;
+            off ^= ((off >> 7) & 7u) << 4;
+            const uint16_t h = f2bf(v);
+            memcpy(tile + off, &h, 2);
+          }
+        }
+      }
+    }
+  return img;
+}
+
+template <int COUT, int EPI>
+int launch_conv_inst(b200sr_engine* e, const CUtensorMap& amap, const ConvArgs& a, cudaStream_t st) {
+  using Cfg = ConvCfg<COUT>;
+  static bool attr_done[16] = {};
+  auto kern = conv3x3_tc_kernel<COUT, EPI>;
+  if (!attr_done[e->device & 15]) {
+    CUDA_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done[e->device & 15] = true;
+  }
+  int grid = std::min(a.ntiles, e->opt_max_ctas > 0 ? e->opt_max_ctas : e->num_sms);
+  kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>>(amap, a);
+  CUDA_TRY(e, cudaGetLastError());
+  e->launches++;
+  return B200SR_OK;
+}
+
+// Rows per tile: fill the 512 TMEM columns unless a smaller TH balances the waves better.
+int choose_th(const b200sr_engine* e, int coutp, int N, int H, int W) {
+  const int maxth = 512 / coutp;
+  if (e->opt_force_th > 0) return std::min(e->opt_force_th, maxth);
+  const int xt = (W + 127) / 128;
+  const int slots = e->opt_max_ctas > 0 ? e->opt_max_ctas : e->num_sms;
+  double best = 1e30;
+  int best_th = maxth;
+  for (int th = maxth; th >= 1; --th) {
+    const long tiles = static_cast<long>(xt) * ((H + th - 1) / th) * N;
+    const long waves = (tiles + slots - 1) / slots;
+    const double cost = static_cast<double>(waves) * (th + 1.0);  // two halo rows cost about one full row
+    if (cost < best - 1e-9) {
+      best = cost;
+      best_th = th;
+    }
+  }
+  return best_th;
+}
+
+struct ConvIO {
+  const void* in;   // bf16 NHWC input tensor
+  int in_pitch;     // channels per pixel
+  int N, H, W;
+};
+
+int launch_conv(b200sr_engine* e, const Layer& l, int epi, const ConvIO& io, ConvArgs a, cudaStream_t st) {
+  CUtensorMap amap;
+  if (!tmap_encode_act(&amap, io.in, io.N, io.H, io.W, io.in_pitch, 64, ConvCfg<64>::A_ROWS, 128))
+    return fail(e, B200SR_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  a.N = io.N;
+  a.H = io.H;
+  a.W = io.W;
+  a.nchunks = (l.cin + 63) / 64;
+  a.last_ksteps = (l.cin % 64 == 32) ? 2 : 4;
+  a.TH = choose_th(e, l.coutp, io.N, io.H, io.W);
+  a.xtiles = (io.W + 127) / 128;
+  a.ytiles = (io.H + a.TH - 1) / a.TH;
+  a.ntiles = a.xtiles * a.ytiles * io.N;
+  a.wpack = l.d_wpack;
+  a.bias = l.d_bias;
+  switch (l.coutp * 16 + epi) {
+    case 32 * 16 + EPI_ACT_BF16: return launch_conv_inst<32, EPI_ACT_BF16>(e, amap, a, st);
+    case 64 * 16 + EPI_ACT_BF16: return launch_conv_inst<64, EPI_ACT_BF16>(e, amap, a, st);
+    case 64 * 16 + EPI_PRELU_BF16: return launch_conv_inst<64, EPI_PRELU_BF16>(e, amap, a, st);
+    case 64 * 16 + EPI_RDB5: return launch_conv_inst<64, EPI_RDB5>(e, amap, a, st);
+    case 64 * 16 + EPI_RDB5_RRDB: return launch_conv_inst<64, EPI_RDB5_RRDB>(e, amap, a, st);
+    case 64 * 16 + EPI_ADD_F32: return launch_conv_inst<64, EPI_ADD_F32>(e, amap, a, st);
+    case 16 * 16 + EPI_LAST_U8: return launch_conv_inst<16, EPI_LAST_U8>(e, amap, a, st);
+    case 48 * 16 + EPI_SRVGG_LAST: return launch_conv_inst<48, EPI_SRVGG_LAST>(e, amap, a, st);
+    default: return fail(e, B200SR_ERR_INVALID, "no kernel instance for this (Cout, epilogue)");
+  }
+}
+
+// ---- workspace layout for one region of conv-domain size N x H x W ----
+struct Region {
+  // source frame + padding
+  const uint8_t* src;
+  uint8_t* dst;
+  int n, Hs, Ws, pre_pad, H1, W1;
+  int oy, ox, rh, rw;          // region in padded-image coordinates
+  int crop_y0, crop_x0, crop_h, crop_w, dst_y0, dst_x0, dst_h, dst_w;  // in network-output pixels
+};
+
+size_t region_ws_bytes(const b200sr_engine* e, int N, int H, int W) {
+  const size_t px = static_cast<size_t>(N) * H * W;
+  size_t total = 0;
+  auto add = [&](size_t b) { total += align_up(b, 1024); };
+  if (e->desc.arch == B200SR_ARCH_RRDB) {
+    add(px * 192 * 2);
+    add(px * 192 * 2);            // dense ping-pong
+    add(px * 64 * 4);
+    add(px * 64 * 4);
+    add(px * 64 * 4);             // xa, xb, f0
+    add(px * 64 * 2);             // conv_body out
+    add(px * 4 * 64 * 2);
+    add(px * 4 * 64 * 2);         // 2x: upsampled, conv_up1 out
+    add(px * 16 * 64 * 2);
+    add(px * 16 * 64 * 2);        // 4x ping-pong
+  } else {
+    add(px * 64 * 2);
+    add(px * 64 * 2);
+    add(px * 4 * 4);
+  }
+  return total;
+}
+
+int ensure_ws(b200sr_engine* e, size_t bytes, cudaStream_t st) {
+  if (bytes <= e->ws_bytes) return B200SR_OK;
+  if (e->ws) {
+    CUDA_TRY(e, cudaStreamSynchronize(st));
+    CUDA_TRY(e, cudaDeviceSynchronize());
+    cudaFree(e->ws);
+    e->ws = nullptr;
+    e->ws_bytes = 0;
+  }
+  void* p = nullptr;
+  cudaError_t err = cudaMalloc(&p, bytes);
+  if (err != cudaSuccess) {
+    cudaGetLastError();
+    return fail(e, B200SR_ERR_OOM, std::string("out of memory allocating ") + std::to_string(bytes >> 20) + " MiB workspace");
+  }
+  e->ws = static_cast<uint8_t*>(p);
+  e->ws_bytes = bytes;
+  return B200SR_OK;
+}
+
+int run_first(b200sr_engine* e, const Region& R, int s, int H, int W, __nv_bfloat16* out, int out_pitch, float* xa,
+              float* xb, float* f0, float* inrgb, const float* prelu, cudaStream_t st) {
+  const Layer& l = e->layers[0];
+  FirstArgs a{};
+  a.src = R.src;
+  a.N = R.n;
+  a.Hs = R.Hs;
+  a.Ws = R.Ws;
+  a.H1 = R.H1;
+  a.W1 = R.W1;
+  a.oy = R.oy;
+  a.ox = R.ox;
+  a.s = s;
+  a.H = H;
+  a.W = W;
+  a.cin = l.cin;
+  a.w = l.d_wfirst;
+  a.bias = l.d_bias;
+  a.prelu = prelu;
+  a.out = out;
+  a.out_pitch = out_pitch;
+  a.xa = xa;
+  a.xb = xb;
+  a.f0 = f0;
+  a.inrgb = inrgb;
+  dim3 grid((W + 127) / 128, H, R.n);
+  if (l.cin == 3) {
+    const size_t sm = 9 * 3 * 64 * sizeof(float);
+    first_conv_kernel<3><<<grid, 128, sm, st>>>(a);
+  } else {
+    const size_t sm = 9 * 12 * 64 * sizeof(float);
+    first_conv_kernel<12><<<grid, 128, sm, st>>>(a);
+  }
+  CUDA_TRY(e, cudaGetLastError());
+  e->launches++;
+  return B200SR_OK;
+}
+
+int run_upsample(b200sr_engine* e, const void* in, void* out, int N, int H, int W, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(N) * 2 * H * 2 * W * 8;
+  const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(e->num_sms) * 16));
+  upsample2x_kernel<<<grid, 256, 0, st>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), N, H, W);
+  CUDA_TRY(e, cudaGetLastError());
+  e->launches++;
+  return B200SR_OK;
+}
+
+// One forward pass over one region (whole padded frame, or one padded tile).
+int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
+  const auto& d = e->desc;
+  const int s = (d.arch == B200SR_ARCH_RRDB && d.scale == 2) ? 2 : 1;
+  if (R.rh % s || R.rw % s) return fail(e, B200SR_ERR_INVALID, "region size not divisible by the unshuffle factor");
+  const int N = R.n, H = R.rh / s, W = R.rw / s;
+  const size_t px = static_cast<size_t>(N) * H * W;
+  int rc = ensure_ws(e, region_ws_bytes(e, N, H, W), st);
+  if (rc) return rc;
+  uint8_t* cur = e->ws;
+  auto take = [&](size_t b) {
+    uint8_t* p = cur;
+    cur += align_up(b, 1024);
+    return p;
+  };
+  ConvArgs base{};
+  base.slope = 1.f;
+  base.dst = R.dst;
+  base.dst_h = R.dst_h;
+  base.dst_w = R.dst_w;
+  base.crop_y0 = R.crop_y0;
+  base.crop_x0 = R.crop_x0;
+  base.crop_h = R.crop_h;
+  base.crop_w = R.crop_w;
+  base.dst_y0 = R.dst_y0;
+  base.dst_x0 = R.dst_x0;
+
+  if (d.arch == B200SR_ARCH_RRDB) {
+    __nv_bfloat16* D[2];
+    D[0] = reinterpret_cast<__nv_bfloat16*>(take(px * 192 * 2));
+    D[1] = reinterpret_cast<__nv_bfloat16*>(take(px * 192 * 2));
+    float* xa = reinterpret_cast<float*>(take(px * 64 * 4));
+    float* xb = reinterpret_cast<float*>(take(px * 64 * 4));
+    float* f0 = reinterpret_cast<float*>(take(px * 64 * 4));
+    __nv_bfloat16* U0 = reinterpret_cast<__nv_bfloat16*>(take(px * 64 * 2));
+    __nv_bfloat16* U1 = reinterpret_cast<__nv_bfloat16*>(take(px * 4 * 64 * 2));
+    __nv_bfloat16* U2 = reinterpret_cast<__nv_bfloat16*>(take(px * 4 * 64 * 2));
+    __nv_bfloat16* U3 = reinterpret_cast<__nv_bfloat16*>(take(px * 16 * 64 * 2));
+    __nv_bfloat16* U4 = reinterpret_cast<__nv_bfloat16*>(take(px * 16 * 64 * 2));
+
+    rc = run_first(e, R, s, H, W, D[0], 192, xa, xb, f0, nullptr, nullptr, st);
+    if (rc) return rc;
+    int li = 1, cur_d = 0;
+    for (int b = 0; b < d.num_block; ++b)
+      for (int r = 0; r < 3; ++r) {
+        ConvIO io{D[cur_d], 192, N, H, W};
+        for (int k = 0; k < 4; ++k) {
+          ConvArgs a = base;
+          a.slope = 0.2f;
+          a.out = D[cur_d];
+          a.out_pitch = 192;
+          a.out_choff = 64 + 32 * k;
+          rc = launch_conv(e, e->layers[li++], EPI_ACT_BF16, io, a, st);
+          if (rc) return rc;
+        }
+        ConvArgs a = base;
+        a.out = D[cur_d ^ 1];
+        a.out_pitch = 192;
+        a.out_choff = 0;
+        a.xa = xa;
+        a.xb = xb;
+        rc = launch_conv(e, e->layers[li++], r == 2 ? EPI_RDB5_RRDB : EPI_RDB5, io, a, st);
+        if (rc) return rc;
+        cur_d ^= 1;
+      }
+    {  // conv_body: feat + conv_body(body(feat))
+      ConvIO io{D[cur_d], 192, N, H, W};
+      ConvArgs a = base;
+      a.out = U0;
+      a.out_pitch = 64;
+      a.fadd = f0;
+      rc = launch_conv(e, e->layers[li++], EPI_ADD_F32, io, a, st);
+      if (rc) return rc;
+    }
+    rc = run_upsample(e, U0, U1, N, H, W, st);
+    if (rc) return rc;
+    {  // conv_up1 + lrelu
+      ConvIO io{U1, 64, N, 2 * H, 2 * W};
+      ConvArgs a = base;
+      a.slope = 0.2f;
+      a.out = U2;
+      a.out_pitch = 64;
+      rc = launch_conv(e, e->layers[li++], EPI_ACT_BF16, io, a, st);
+      if (rc) return rc;
+    }
+    rc = run_upsample(e, U2, U3, N, 2 * H, 2 * W, st);
+    if (rc) return rc;
+    {  // conv_up2 + lrelu
+      ConvIO io{U3, 64, N, 4 * H, 4 * W};
+      ConvArgs a = base;
+      a.slope = 0.2f;
+      a.out = U4;
+      a.out_pitch = 64;
+      rc = launch_conv(e, e->layers[li++], EPI_ACT_BF16, io, a, st);
+      if (rc) return rc;
+    }
+    {  // conv_hr + lrelu
+      ConvIO io{U4, 64, N, 4 * H, 4 * W};
+      ConvArgs a = base;
+      a.slope = 0.2f;
+      a.out = U3;
+      a.out_pitch = 64;
+      rc = launch_conv(e, e->layers[li++], EPI_ACT_BF16, io, a, st);
+      if (rc) return rc;
+    }
+    {  // conv_last + clamp/round/quantise + crop
+      ConvIO io{U3, 64, N, 4 * H, 4 * W};
+      rc = launch_conv(e, e->layers[li++], EPI_LAST_U8, io, base, st);
+      if (rc) return rc;
+    }
+  } else {
+    __nv_bfloat16* S[2];
+    S[0] = reinterpret_cast<__nv_bfloat16*>(take(px * 64 * 2));
+    S[1] = reinterpret_cast<__nv_bfloat16*>(take(px * 64 * 2));
+    float* inrgb = reinterpret_cast<float*>(take(px * 4 * 4));
+    rc = run_first(e, R, 1, H, W, S[0], 64, nullptr, nullptr, nullptr, inrgb, e->prelu_dev[0], st);
+    if (rc) return rc;
+    int cur_s = 0;
+    for (int i = 0; i < d.num_block; ++i) {
+      ConvIO io{S[cur_s], 64, N, H, W};
+      ConvArgs a = base;
+      a.out = S[cur_s ^ 1];
+      a.out_pitch = 64;
+      a.prelu = e->prelu_dev[i + 1];
+      rc = launch_conv(e, e->layers[1 + i], EPI_PRELU_BF16, io, a, st);
+      if (rc) return rc;
+      cur_s ^= 1;
+    }
+    ConvIO io{S[cur_s], 64, N, H, W};
+    ConvArgs a = base;
+    a.fadd = inrgb;
+    rc = launch_conv(e, e->layers[1 + d.num_block], EPI_SRVGG_LAST, io, a, st);
+    if (rc) return rc;
+  }
+  return B200SR_OK;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+const char* b200sr_version(void) { return "b200sr 0.1 (sm_100a, tcgen05/TMEM/TMA)"; }
+
+const char* b200sr_last_error(const b200sr_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+int b200sr_create(const b200sr_model_desc* desc, int device, b200sr_engine** out) {
+  if (!desc || !out) return B200SR_ERR_INVALID;
+  *out = nullptr;
+  if (desc->num_feat != 64 || desc->num_grow_ch != 32 || desc->num_block < 1) return B200SR_ERR_INVALID;
+  if (desc->arch == B200SR_ARCH_RRDB) {
+    if (desc->scale != 4 && desc->scale != 2) return B200SR_ERR_INVALID;
+  } else if (desc->arch == B200SR_ARCH_SRVGG) {
+    if (desc->scale != 4) return B200SR_ERR_INVALID;
+  } else {
+    return B200SR_ERR_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return B200SR_ERR_CUDA;  // no CUDA device: the product path has no CPU fallback
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return B200SR_ERR_CUDA;
+  if (prop.major != 10) return B200SR_ERR_CUDA;  // kernels are sm_100a only
+  auto* e = new b200sr_engine();
+  e->desc = *desc;
+  e->device = device;
+  e->num_sms = prop.multiProcessorCount;
+  build_layers(e);
+  if (cudaSetDevice(device) != cudaSuccess || !tmap_init()) {
+    delete e;
+    return B200SR_ERR_CUDA;
+  }
+  *out = e;
+  return B200SR_OK;
+}
+
+void b200sr_destroy(b200sr_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (auto& l : e->layers) {
+    if (l.d_wpack) cudaFree(l.d_wpack);
+    if (l.d_wfirst) cudaFree(l.d_wfirst);
+    if (l.d_bias) cudaFree(l.d_bias);
+  }
+  for (auto* p : e->prelu_dev)
+    if (p) cudaFree(p);
+  if (e->ws) cudaFree(e->ws);
+  if (e->stage_in) cudaFree(e->stage_in);
+  if (e->stage_out) cudaFree(e->stage_out);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  delete e;
+}
+
+int b200sr_num_convs(const b200sr_engine* e) { return e ? static_cast<int>(e->layers.size()) : 0; }
+int b200sr_num_prelus(const b200sr_engine* e) { return e ? static_cast<int>(e->prelu_host.size()) : 0; }
+
+int b200sr_set_conv(b200sr_engine* e, int layer, const float* weight, const float* bias, int cout, int cin) {
+  if (!e || !weight || !bias) return B200SR_ERR_INVALID;
+  if (layer < 0 || layer >= static_cast<int>(e->layers.size())) return fail(e, B200SR_ERR_INVALID, "layer index out of range");
+  Layer& l = e->layers[layer];
+  if (l.cin != cin || l.cout != cout)
+    return fail(e, B200SR_ERR_INVALID, "conv " + std::to_string(layer) + ": expected [" + std::to_string(l.cout) + "," +
+                                           std::to_string(l.cin) + ",3,3], got [" + std::to_string(cout) + "," +
+                                           std::to_string(cin) + ",3,3]");
+  l.w.assign(weight, weight + static_cast<size_t>(cout) * cin * 9);
+  l.b.assign(bias, bias + cout);
+  l.set = true;
+  e->finalized = false;
+  return B200SR_OK;
+}
+
+int b200sr_set_prelu(b200sr_engine* e, int index, const float* slope, int n) {
+  if (!e || !slope) return B200SR_ERR_INVALID;
+  if (index < 0 || index >= static_cast<int>(e->prelu_host.size()) || n != e->desc.num_feat)
+    return fail(e, B200SR_ERR_INVALID, "bad prelu index / size");
+  e->prelu_host[index].assign(slope, slope + n);
+  e->finalized = false;
+  return B200SR_OK;
+}
+
+int b200sr_finalize(b200sr_engine* e) {
+  if (!e) return B200SR_ERR_INVALID;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  for (size_t i = 0; i < e->layers.size(); ++i) {
+    Layer& l = e->layers[i];
+    if (!l.set) return fail(e, B200SR_ERR_STATE, "conv " + std::to_string(i) + " has no weights");
+    std::vector<float> bias(l.coutp, 0.f);
+    std::copy(l.b.begin(), l.b.end(), bias.begin());
+    if (!l.d_bias) CUDA_TRY(e, cudaMalloc(&l.d_bias, bias.size() * 4));
+    CUDA_TRY(e, cudaMemcpy(l.d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+    if (i == 0) {
+      std::vector<float> wf(static_cast<size_t>(9) * l.cin * 64);
+      for (int co = 0; co < 64; ++co)
+        for (int ci = 0; ci < l.cin; ++ci)
+          for (int t = 0; t < 9; ++t) wf[(static_cast<size_t>(t) * l.cin + ci) * 64 + co] = l.w[(static_cast<size_t>(co) * l.cin + ci) * 9 + t];
+      if (!l.d_wfirst) CUDA_TRY(e, cudaMalloc(&l.d_wfirst, wf.size() * 4));
+      CUDA_TRY(e, cudaMemcpy(l.d_wfirst, wf.data(), wf.size() * 4, cudaMemcpyHostToDevice));
+    } else {
+      std::vector<uint8_t> img = pack_weights(l);
+      if (!l.d_wpack) CUDA_TRY(e, cudaMalloc(&l.d_wpack, img.size()));
+      CUDA_TRY(e, cudaMemcpy(l.d_wpack, img.data(), img.size(), cudaMemcpyHostToDevice));
+    }
+  }
+  for (size_t i = 0; i < e->prelu_host.size(); ++i) {
+    if (e->prelu_host[i].empty()) return fail(e, B200SR_ERR_STATE, "prelu " + std::to_string(i) + " has no weights");
+    if (!e->prelu_dev[i]) CUDA_TRY(e, cudaMalloc(&e->prelu_dev[i], 64 * 4));
+    CUDA_TRY(e, cudaMemcpy(e->prelu_dev[i], e->prelu_host[i].data(), 64 * 4, cudaMemcpyHostToDevice));
+  }
+  e->finalized = true;
+  return B200SR_OK;
+}
+
+int b200sr_output_dims(const b200sr_engine* e, int h, int w, int* out_h, int* out_w) {
+  if (!e || !out_h || !out_w || h <= 0 || w <= 0) return B200SR_ERR_INVALID;
+  *out_h = h * e->desc.scale;
+  *out_w = w * e->desc.scale;
+  return B200SR_OK;
+}
+
+static void padded_dims(const b200sr_engine* e, int h, int w, int pre_pad, int* Hp, int* Wp) {
+  int H1 = h + pre_pad, W1 = w + pre_pad;
+  const int mod = (e->desc.arch == B200SR_ARCH_RRDB && e->desc.scale == 2) ? 2 : 1;
+  *Hp = (H1 + mod - 1) / mod * mod;
+  *Wp = (W1 + mod - 1) / mod * mod;
+}
+
+int b200sr_workspace_bytes(b200sr_engine* e, int n, int h, int w, int tile, int tile_pad, int pre_pad, size_t* bytes) {
+  if (!e || !bytes || n <= 0 || h <= 0 || w <= 0 || tile < 0 || tile_pad < 0 || pre_pad < 0) return B200SR_ERR_INVALID;
+  int Hp, Wp;
+  padded_dims(e, h, w, pre_pad, &Hp, &Wp);
+  const int s = (e->desc.arch == B200SR_ARCH_RRDB && e->desc.scale == 2) ? 2 : 1;
+  int rh = Hp, rw = Wp;
+  if (tile > 0) {
+    rh = std::min(Hp, tile + 2 * tile_pad);
+    rw = std::min(Wp, tile + 2 * tile_pad);
+  }
+  *bytes = region_ws_bytes(e, n, (rh + s - 1) / s, (rw + s - 1) / s);
+  return B200SR_OK;
+}
+
+int b200sr_enqueue_u8(b200sr_engine* e, const uint8_t* src_dev, uint8_t* dst_dev, int n, int h, int w, int tile,
+                      int tile_pad, int pre_pad, void* cuda_stream) {
+  if (!e) return B200SR_ERR_INVALID;
+  if (!e->finalized) return fail(e, B200SR_ERR_STATE, "weights not finalised");
+  if (!src_dev || !dst_dev || n <= 0 || h <= 0 || w <= 0 || tile < 0 || tile_pad < 0 || pre_pad < 0)
+    return fail(e, B200SR_ERR_INVALID, "bad argument");
+  if (pre_pad >= h || pre_pad >= w) return fail(e, B200SR_ERR_INVALID, "pre_pad must be smaller than the frame (reflect padding)");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  e->launches = 0;
+  const int scale = e->desc.scale;
+  int Hp, Wp;
+  padded_dims(e, h, w, pre_pad, &Hp, &Wp);
+  if ((Hp > h + pre_pad && h + pre_pad < 2) || (Wp > w + pre_pad && w + pre_pad < 2))
+    return fail(e, B200SR_ERR_INVALID, "frame too small for reflect mod-padding");
+  Region R{};
+  R.src = src_dev;
+  R.dst = dst_dev;
+  R.n = n;
+  R.Hs = h;
+  R.Ws = w;
+  R.pre_pad = pre_pad;
+  R.H1 = h + pre_pad;
+  R.W1 = w + pre_pad;
+  R.dst_h = h * scale;
+  R.dst_w = w * scale;
+  if (tile == 0) {
+    R.oy = 0;
+    R.ox = 0;
+    R.rh = Hp;
+    R.rw = Wp;
+    R.crop_y0 = 0;
+    R.crop_x0 = 0;
+    R.crop_h = h * scale;
+    R.crop_w = w * scale;
+    R.dst_y0 = 0;
+    R.dst_x0 = 0;
+    return run_region(e, R, st);
+  }
+  // upstream RealESRGANer.tile_process over the padded image
+  const int tiles_x = (Wp + tile - 1) / tile, tiles_y = (Hp + tile - 1) / tile;
+  for (int ty = 0; ty < tiles_y; ++ty)
+    for (int tx = 0; tx < tiles_x; ++tx) {
+      const int in_x0 = tx * tile, in_y0 = ty * tile;
+      const int in_x1 = std::min(in_x0 + tile, Wp), in_y1 = std::min(in_y0 + tile, Hp);
+      const int pad_x0 = std::max(in_x0 - tile_pad, 0), pad_x1 = std::min(in_x1 + tile_pad, Wp);
+      const int pad_y0 = std::max(in_y0 - tile_pad, 0), pad_y1 = std::min(in_y1 + tile_pad, Hp);
+      R.oy = pad_y0;
+      R.ox = pad_x0;
+      R.rh = pad_y1 - pad_y0;
+      R.rw = pad_x1 - pad_x0;
+      R.crop_y0 = (in_y0 - pad_y0) * scale;
+      R.crop_x0 = (in_x0 - pad_x0) * scale;
+      R.dst_y0 = in_y0 * scale;
+      R.dst_x0 = in_x0 * scale;
+      R.crop_h = std::min((in_y1 - in_y0) * scale, R.dst_h - R.dst_y0);  // post_process crop of the pads
+      R.crop_w = std::min((in_x1 - in_x0) * scale, R.dst_w - R.dst_x0);
+      if (R.crop_h <= 0 || R.crop_w <= 0) continue;
+      const int launches_before = e->launches;
+      int rc = run_region(e, R, st);
+      if (rc) return rc;
+      (void)launches_before;
+    }
+  return B200SR_OK;
+}
+
+int b200sr_upscale_host_u8(b200sr_engine* e, const uint8_t* src_host, uint8_t* dst_host, int n, int h, int w, int tile,
+                           int tile_pad, int pre_pad) {
+  if (!e || !src_host || !dst_host || n <= 0 || h <= 0 || w <= 0) return B200SR_ERR_INVALID;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  if (!e->own_stream) CUDA_TRY(e, cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  const size_t in_bytes = static_cast<size_t>(n) * h * w * 3;
+  const size_t out_bytes = in_bytes * e->desc.scale * e->desc.scale;
+  if (in_bytes > e->stage_in_bytes) {
+    if (e->stage_in) cudaFree(e->stage_in);
+    e->stage_in = nullptr;
+    e->stage_in_bytes = 0;
+    CUDA_TRY(e, cudaMalloc(&e->stage_in, in_bytes));
+    e->stage_in_bytes = in_bytes;
+  }
+  if (out_bytes > e->stage_out_bytes) {
+    if (e->stage_out) cudaFree(e->stage_out);
+    e->stage_out = nullptr;
+    e->stage_out_bytes = 0;
+    CUDA_TRY(e, cudaMalloc(&e->stage_out, out_bytes));
+    e->stage_out_bytes = out_bytes;
+  }
+  CUDA_TRY(e, cudaMemcpyAsync(e->stage_in, src_host, in_bytes, cudaMemcpyHostToDevice, e->own_stream));
+  int rc = b200sr_enqueue_u8(e, e->stage_in, e->stage_out, n, h, w, tile, tile_pad, pre_pad, e->own_stream);
+  if (rc) return rc;
+  CUDA_TRY(e, cudaMemcpyAsync(dst_host, e->stage_out, out_bytes, cudaMemcpyDeviceToHost, e->own_stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->own_stream));
+  return B200SR_OK;
+}
+
+int b200sr_last_launch_count(const b200sr_engine* e) { return e ? e->launches : 0; }
+
+int b200sr_set_option(b200sr_engine* e, const char* key, int value) {
+  if (!e || !key) return B200SR_ERR_INVALID;
+  if (!strcmp(key, "force_th")) {
+    e->opt_force_th = value;
+    return B200SR_OK;
+  }
+  if (!strcmp(key, "max_ctas")) {
+    e->opt_max_ctas = value;
+    return B200SR_OK;
+  }
+  return fail(e, B200SR_ERR_INVALID, std::string("unknown option ") + key);
+}
+
+// ---- test hook: one tensor-core conv layer on caller-provided device tensors -------------------
+// in: bf16 NHWC [n][h][w][in_pitch]; weight fp32 OIHW host; out: bf16 NHWC [n][h][w][out_pitch].
+// epi: 0 = leaky(slope) -> bf16 slice ; 1 = prelu(prelu_host) -> bf16.
+int b200sr_debug_conv3x3(int device, const void* in_dev, int n, int h, int w, int in_pitch, int cin,
+                         const float* weight, const float* bias, int cout, int epi, float slope,
+                         const float* prelu_host, void* out_dev, int out_pitch, int out_choff, int force_th,
+                         int max_ctas, void* cuda_stream, char* errbuf, int errbuf_len) {
+  b200sr_engine e;
+  e.device = device;
+  auto report = [&](int rc) {
+    if (errbuf && errbuf_len > 0) snprintf(errbuf, errbuf_len, "%s", e.err.c_str());
+    return rc;
+  };
+  if (cudaSetDevice(device) != cudaSuccess) return report(fail(&e, B200SR_ERR_CUDA, "cudaSetDevice failed"));
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+    return report(fail(&e, B200SR_ERR_CUDA, "needs an sm_100 device"));
+  e.num_sms = prop.multiProcessorCount;
+  e.opt_force_th = force_th;
+  e.opt_max_ctas = max_ctas;
+  if (!tmap_init()) return report(fail(&e, B200SR_ERR_CUDA, "no cuTensorMapEncodeTiled"));
+  if (cin % 32 || cin < 32 || cin > in_pitch) return report(fail(&e, B200SR_ERR_INVALID, "cin must be a multiple of 32 and <= in_pitch"));
+  Layer l;
+  l.cin = cin;
+  l.cout = cout;
+  l.coutp = coutp_for(cout);
+  if (!((l.coutp == 32 && epi == 0) || (l.coutp == 64 && (epi == 0 || epi == 1))))
+    return report(fail(&e, B200SR_ERR_INVALID, "debug conv supports Cout 32 (leaky) and 64 (leaky / prelu)"));
+  l.w.assign(weight, weight + static_cast<size_t>(cout) * cin * 9);
+  l.b.assign(bias, bias + cout);
+  std::vector<uint8_t> img = pack_weights(l);
+  std::vector<float> bp(l.coutp, 0.f);
+  std::copy(l.b.begin(), l.b.end(), bp.begin());
+  float* d_prelu = nullptr;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  int rc = B200SR_OK;
+  auto body = [&]() -> int {
+    CUDA_TRY(&e, cudaMalloc(&l.d_wpack, img.size()));
+    CUDA_TRY(&e, cudaMalloc(&l.d_bias, bp.size() * 4));
+    CUDA_TRY(&e, cudaMemcpy(l.d_wpack, img.data(), img.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(&e, cudaMemcpy(l.d_bias, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
+    ConvArgs a{};
+    a.slope = slope;
+    a.out = static_cast<__nv_bfloat16*>(out_dev);
+    a.out_pitch = out_pitch;
+    a.out_choff = out_choff;
+    if (epi == 1) {
+      if (!prelu_host) return fail(&e, B200SR_ERR_INVALID, "prelu slopes missing");
+      CUDA_TRY(&e, cudaMalloc(&d_prelu, 64 * 4));
+      CUDA_TRY(&e, cudaMemcpy(d_prelu, prelu_host, 64 * 4, cudaMemcpyHostToDevice));
+      a.prelu = d_prelu;
+    }
+    ConvIO io{in_dev, in_pitch, n, h, w};
+    int r = launch_conv(&e, l, epi == 1 ? EPI_PRELU_BF16 : EPI_ACT_BF16, io, a, st);
+    if (r) return r;
+    CUDA_TRY(&e, cudaStreamSynchronize(st));
+    return B200SR_OK;
+  };
+  rc = body();
+  if (l.d_wpack) cudaFree(l.d_wpack);
+  if (l.d_bias) cudaFree(l.d_bias);
+  if (d_prelu) cudaFree(d_prelu);
+  return report(rc);
+}
+
+}  // extern "C"

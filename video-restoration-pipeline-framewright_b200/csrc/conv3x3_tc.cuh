@@ -1,0 +1,416 @@
+// 3x3 / stride 1 / pad 1 convolution as an implicit GEMM on the sm_100a tensor cores.
+//
+// Replaces (per layer) what the reference executes through PyTorch -> cuDNN inside
+// `RRDBNet.forward` / `SRVGGNetCompact.forward` (constructed at
+// /root/reference/src/framewright/processors/pytorch_realesrgan.py:107-127, run by
+// `upsampler.enhance` at :223), together with the elementwise ops that follow each conv
+// (bias, LeakyReLU/PReLU, torch.cat, the 0.2 residual scalings, clamp/round/quantise).
+//
+// Formulation ("row streaming, accumulator stationary"):
+//   * NHWC bf16 activations; a CTA owns an output tile of 128 pixels (one image-row segment)
+//     x TH rows.  GEMM M = the 128 pixels, N = output channels, K = input channels x taps.
+//   * One TMA box = one input row segment [130 px][64 ch] (128-byte rows, SWIZZLE_128B).
+//     The three horizontal taps are three row-shifted UMMA descriptor views of that single
+//     box (start address + dx*128 B; hardware swizzle is a function of the absolute smem
+//     address, verified by csrc/tools/probe_umma.cu), so every activation byte is staged
+//     into shared memory exactly once.  Zero padding at the image (or tile) border is the
+//     TMA out-of-bounds fill.
+//   * The three vertical taps are stacked along N: input row y feeds output rows y-1, y, y+1,
+//     whose fp32 accumulators sit in adjacent TMEM column blocks, so one
+//     tcgen05.mma M128 x N(3*Cout) x K16 updates all three (A is read from smem once per
+//     3*Cout columns instead of once per Cout: the SS-mode smem read of A is the bound for
+//     N <= 128).
+//   * All TH accumulator rows (TH*Cout <= 512 TMEM columns) stay resident while the input
+//     channels are swept in 64-wide chunks (weights of one chunk resident in smem, double
+//     buffered).  Rows finish one by one during the last chunk; per-row full/empty
+//     mbarriers let the epilogue warps drain row Y while the MMA warp is already working on
+//     later rows / the next tile.
+//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 =
+//     epilogue (TMEM -> registers -> fused pointwise -> global).
+#pragma once
+#include <cuda_bf16.h>
+#include "ptx.cuh"
+
+namespace b200sr {
+
+enum EpiMode : int {
+  EPI_ACT_BF16 = 0,   // y = act(acc + b), act = leaky(slope) (slope = 1 -> identity); bf16 slice store
+  EPI_PRELU_BF16,     // y = prelu(acc + b, a[c]); bf16 store
+  EPI_RDB5,           // x <- (acc + b) * 0.2 + x        (fp32 trunk in place, + bf16 copy)
+  EPI_RDB5_RRDB,      // x <- ((acc + b) * 0.2 + x) * 0.2 + x0 ; x0 <- x   (+ bf16 copy)
+  EPI_ADD_F32,        // y = acc + b + f[c]; bf16 store   (conv_body: feat + body_feat)
+  EPI_LAST_U8,        // 3 real channels: clamp(acc + b, 0, 1) -> round(255 v) -> u8 BGR (cropped)
+  EPI_SRVGG_LAST      // 48 ch: pixel-shuffle(4) + nearest(x) residual -> clamp/round -> u8 BGR
+};
+
+struct ConvArgs {
+  int N, H, W;        // spatial extent of this conv (input == output)
+  int nchunks;        // ceil(Cin / 64)
+  int last_ksteps;    // K16 steps in the last chunk: 4, or 2 when Cin % 64 == 32
+  int TH;             // output rows per tile, <= 512 / COUT
+  int xtiles, ytiles, ntiles;
+  const uint8_t* wpack;   // packed weights: [chunk][dx][3*COUT rows][128 B] (SWIZZLE_128B image)
+  const float* bias;      // COUT floats
+  const float* prelu;     // COUT floats (EPI_PRELU_BF16)
+  float slope;            // leaky slope (EPI_ACT_BF16)
+  __nv_bfloat16* out;     // bf16 NHWC destination
+  int out_pitch;          // channels per pixel in `out`
+  int out_choff;          // first channel written
+  float* xa;              // fp32 trunk (RDB input / output, in place)
+  float* xb;              // fp32 RRDB-level skip
+  const float* fadd;      // fp32 addend (EPI_ADD_F32) / normalised network input RGBx (EPI_SRVGG_LAST)
+  uint8_t* dst;           // u8 BGR destination frame(s)  [N][dst_h][dst_w][3]
+  int dst_h, dst_w;       // destination frame size
+  int crop_y0, crop_x0;   // first conv-output pixel kept
+  int crop_h, crop_w;     // kept extent
+  int dst_y0, dst_x0;     // where the kept window lands in the destination frame
+};
+
+template <int COUT>
+struct ConvCfg {
+  static constexpr int MAXTH = 512 / COUT;
+  static constexpr int WTILE_BYTES = 3 * COUT * 128;    // (chunk, dx): 3 dy-blocks x COUT rows x 128 B
+  static constexpr int WCHUNK_BYTES = 3 * WTILE_BYTES;
+  static constexpr int A_ROWS = 130;
+  static constexpr int A_BOX_BYTES = A_ROWS * 128;
+  static constexpr int A_STAGE_BYTES = 17 * 1024;
+  static constexpr int NSTAGES = (COUT >= 48) ? 4 : 6;
+  static constexpr int SMEM_BYTES = 2 * WCHUNK_BYTES + NSTAGES * A_STAGE_BYTES + 1024 /*align slack*/;
+  static constexpr int NTHREADS = 192;
+};
+
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint8_t quant_u8(float v) {
+  v = fminf(fmaxf(v, 0.f), 1.f);
+  return static_cast<uint8_t>(__float2int_rn(v * 255.0f));
+}
+
+// Load this thread's COUT accumulator columns of one tile row.
+template <int COUT>
+__device__ __forceinline__ void load_acc_row(uint32_t taddr, float (&acc)[COUT]) {
+  if constexpr (COUT == 16) {
+    uint32_t v[16];
+    tmem_ld16(taddr, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[i]);
+  } else if constexpr (COUT == 32) {
+    uint32_t v[32];
+    tmem_ld32(taddr, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(v[i]);
+  } else if constexpr (COUT == 48) {
+    uint32_t v[32], w[16];
+    tmem_ld32(taddr, v);
+    tmem_ld16(taddr + 32, w);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(v[i]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[32 + i] = __uint_as_float(w[i]);
+  } else {
+    static_assert(COUT == 64, "unsupported COUT");
+    uint32_t v[32], w[32];
+    tmem_ld32(taddr, v);
+    tmem_ld32(taddr + 32, w);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(v[i]);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[32 + i] = __uint_as_float(w[i]);
+  }
+}
+
+template <int COUT>
+__device__ __forceinline__ void store_bf16_row(__nv_bfloat16* dst, const float (&v)[COUT]) {
+#pragma unroll
+  for (int g = 0; g < COUT / 16; ++g) {
+    uint32_t p[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = pack_bf16x2(v[g * 16 + 2 * i], v[g * 16 + 2 * i + 1]);
+    st_global_256(dst + g * 16, p);
+  }
+}
+
+// Fused pointwise tail of one output pixel (one thread).
+template <int COUT, int EPI>
+__device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* s_bias, const float* s_prelu,
+                                               float (&acc)[COUT], int n, int y, int x) {
+  const size_t pix = (static_cast<size_t>(n) * a.H + y) * a.W + x;
+  if constexpr (EPI == EPI_ACT_BF16) {
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) {
+      float v = acc[c] + s_bias[c];
+      acc[c] = v > 0.f ? v : v * a.slope;
+    }
+    store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc);
+  } else if constexpr (EPI == EPI_PRELU_BF16) {
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) {
+      float v = acc[c] + s_bias[c];
+      acc[c] = v > 0.f ? v : v * s_prelu[c];
+    }
+    store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc);
+  } else if constexpr (EPI == EPI_RDB5 || EPI == EPI_RDB5_RRDB) {
+    float* xa = a.xa + pix * COUT;
+    float* xb = a.xb + pix * COUT;
+#pragma unroll
+    for (int g = 0; g < COUT / 8; ++g) {
+      uint32_t r[8];
+      ld_global_256(xa + g * 8, r);
+      uint32_t o[8];
+      if constexpr (EPI == EPI_RDB5_RRDB) {
+        uint32_t r0[8];
+        ld_global_256(xb + g * 8, r0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float v = (acc[g * 8 + i] + s_bias[g * 8 + i]) * 0.2f + __uint_as_float(r[i]);
+          v = v * 0.2f + __uint_as_float(r0[i]);
+          acc[g * 8 + i] = v;
+          o[i] = __float_as_uint(v);
+        }
+        st_global_256(xb + g * 8, o);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float v = (acc[g * 8 + i] + s_bias[g * 8 + i]) * 0.2f + __uint_as_float(r[i]);
+          acc[g * 8 + i] = v;
+          o[i] = __float_as_uint(v);
+        }
+      }
+      st_global_256(xa + g * 8, o);
+    }
+    store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc);
+  } else if constexpr (EPI == EPI_ADD_F32) {
+    const float* f = a.fadd + pix * COUT;
+#pragma unroll
+    for (int g = 0; g < COUT / 8; ++g) {
+      uint32_t r[8];
+      ld_global_256(f + g * 8, r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[g * 8 + i] = acc[g * 8 + i] + s_bias[g * 8 + i] + __uint_as_float(r[i]);
+    }
+    store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc);
+  } else if constexpr (EPI == EPI_LAST_U8) {
+    const int cy = y - a.crop_y0, cx = x - a.crop_x0;
+    if (cy >= 0 && cy < a.crop_h && cx >= 0 && cx < a.crop_w) {
+      uint8_t* d = a.dst + ((static_cast<size_t>(n) * a.dst_h + (a.dst_y0 + cy)) * a.dst_w + (a.dst_x0 + cx)) * 3;
+      d[0] = quant_u8(acc[2] + s_bias[2]);  // B
+      d[1] = quant_u8(acc[1] + s_bias[1]);  // G
+      d[2] = quant_u8(acc[0] + s_bias[0]);  // R
+    }
+  } else {
+    static_assert(EPI == EPI_SRVGG_LAST && COUT == 48, "SRVGG tail needs 48 channels");
+    const float4 in = *reinterpret_cast<const float4*>(a.fadd + pix * 4);  // normalised RGB of this LR pixel
+    const float base[3] = {in.x, in.y, in.z};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int cy = y * 4 + i - a.crop_y0;
+      if (cy < 0 || cy >= a.crop_h) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cx = x * 4 + j - a.crop_x0;
+        if (cx < 0 || cx >= a.crop_w) continue;
+        uint8_t* d = a.dst + ((static_cast<size_t>(n) * a.dst_h + (a.dst_y0 + cy)) * a.dst_w + (a.dst_x0 + cx)) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int o = c * 16 + i * 4 + j;
+          d[2 - c] = quant_u8(acc[o] + s_bias[o] + base[c]);
+        }
+      }
+    }
+  }
+}
+
+template <int COUT, int EPI>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args) {
+  using Cfg = ConvCfg<COUT>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;                              // 2 x WCHUNK_BYTES
+  uint8_t* sA = smem + 2 * Cfg::WCHUNK_BYTES;      // NSTAGES x A_STAGE_BYTES
+
+  __shared__ uint64_t bar_full[Cfg::NSTAGES], bar_empty[Cfg::NSTAGES];
+  __shared__ uint64_t bar_wfull[2], bar_wempty[2];
+  __shared__ uint64_t bar_rfull[Cfg::MAXTH], bar_rempty[Cfg::MAXTH];
+  __shared__ uint32_t s_tmem_base;
+  __shared__ float s_bias[COUT];
+  __shared__ float s_prelu[COUT];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int TH = args.TH;
+
+  if (threadIdx.x < COUT) {
+    s_bias[threadIdx.x] = args.bias[threadIdx.x];
+    s_prelu[threadIdx.x] = (EPI == EPI_PRELU_BF16) ? args.prelu[threadIdx.x] : 0.f;
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::NSTAGES; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_wfull[i], 1);
+      mbar_init(&bar_wempty[i], 1);
+    }
+    for (int i = 0; i < Cfg::MAXTH; ++i) {
+      mbar_init(&bar_rfull[i], 1);
+      mbar_init(&bar_rempty[i], 4);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&amap);
+  }
+  if (warp == 1) {
+    tmem_alloc(&s_tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  const int tiles_per_img = args.xtiles * args.ytiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0, phase = 0, wb = 0, wphase = 0;
+      for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
+        const int n = t / tiles_per_img;
+        const int r = t - n * tiles_per_img;
+        const int ty = r / args.xtiles;
+        const int tx = r - ty * args.xtiles;
+        const int x0 = tx * 128 - 1;
+        const int y0 = ty * TH;
+        for (int c = 0; c < args.nchunks; ++c) {
+          mbar_wait(&bar_wempty[wb], wphase ^ 1);
+          mbar_arrive_expect_tx(&bar_wfull[wb], Cfg::WCHUNK_BYTES);
+          const uint8_t* wsrc = args.wpack + static_cast<size_t>(c) * Cfg::WCHUNK_BYTES;
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+            bulk_load_1d(&bar_wfull[wb], sW + wb * Cfg::WCHUNK_BYTES + d * Cfg::WTILE_BYTES,
+                         wsrc + d * Cfg::WTILE_BYTES, Cfg::WTILE_BYTES);
+          for (int y = -1; y <= TH; ++y) {
+            mbar_wait(&bar_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&bar_full[stage], Cfg::A_BOX_BYTES);
+            tma_load_4d(&amap, &bar_full[stage], sA + stage * Cfg::A_STAGE_BYTES, c * 64, x0, y0 + y, n);
+            if (++stage == Cfg::NSTAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          wb ^= 1;
+          if (wb == 0) wphase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc_bf16(128, COUT);
+      const uint32_t idesc2 = make_idesc_bf16(128, 2 * COUT);
+      const uint32_t idesc3 = make_idesc_bf16(128, 3 * COUT);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(sA), 1024, SWZ_128B, 0);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(sW), 1024, SWZ_128B, 0);
+      int stage = 0, phase = 0, wb = 0, wphase = 0;
+      uint32_t tile_iter = 0;
+      for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x, ++tile_iter) {
+        const uint32_t rparity = (tile_iter & 1) ^ 1;  // accumulator row drained by the previous tile's epilogue
+        for (int c = 0; c < args.nchunks; ++c) {
+          const int ks = (c == args.nchunks - 1) ? args.last_ksteps : 4;
+          const bool first_chunk = (c == 0);
+          const bool last_chunk = (c == args.nchunks - 1);
+          mbar_wait(&bar_wfull[wb], wphase);
+          const uint64_t bdesc_w = bdesc0 + static_cast<uint64_t>((wb * Cfg::WCHUNK_BYTES) >> 4);
+          for (int y = -1; y <= TH; ++y) {
+            const int blk_lo = (y < 1) ? (1 - y) : 0;        // output row y-1+blk must be >= 0
+            const int blk_hi = (TH - y < 2) ? (TH - y) : 2;  // and < TH
+            const int nblk = blk_hi - blk_lo + 1;
+            if (first_chunk && blk_hi == 2) mbar_wait(&bar_rempty[y + 1], rparity);
+            mbar_wait(&bar_full[stage], phase);
+            tc_fence_after();
+            const uint32_t dcol = tmem_base + static_cast<uint32_t>((y - 1 + blk_lo) * COUT);
+            const uint64_t ad0 = adesc0 + static_cast<uint64_t>((stage * Cfg::A_STAGE_BYTES) >> 4);
+            const uint64_t bd0 = bdesc_w + static_cast<uint64_t>((blk_lo * COUT * 128) >> 4);
+            const uint32_t idesc_n = nblk == 3 ? idesc3 : (nblk == 2 ? idesc2 : idesc1);
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < ks) {
+                  const uint64_t ad = ad0 + static_cast<uint64_t>((dx * 128 + k * 32) >> 4);
+                  const uint64_t bd = bd0 + static_cast<uint64_t>((dx * Cfg::WTILE_BYTES + k * 32) >> 4);
+                  if (dx == 0 && k == 0 && first_chunk && blk_hi == 2) {
+                    // accumulator row y+1 is touched for the first time: overwrite it, accumulate the others
+                    if (nblk > 1) umma_bf16(dcol, ad, bd, nblk == 3 ? idesc2 : idesc1, 1);
+                    umma_bf16(dcol + (nblk - 1) * COUT, ad, bd + static_cast<uint64_t>(((nblk - 1) * COUT * 128) >> 4),
+                              idesc1, 0);
+                  } else {
+                    umma_bf16(dcol, ad, bd, idesc_n, 1);
+                  }
+                }
+              }
+            }
+            umma_commit(&bar_empty[stage]);                               // stage reusable once these MMAs retire
+            if (last_chunk && y >= 1) umma_commit(&bar_rfull[y - 1]);     // output row y-1 is complete
+            if (++stage == Cfg::NSTAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit(&bar_wempty[wb]);
+          wb ^= 1;
+          if (wb == 0) wphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (2..5)
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;             // pixel within the 128-wide tile == TMEM lane
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t tile_iter = 0;
+    for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x, ++tile_iter) {
+      const int n = t / tiles_per_img;
+      const int r = t - n * tiles_per_img;
+      const int ty = r / args.xtiles;
+      const int tx = r - ty * args.xtiles;
+      const int x = tx * 128 + m;
+      const int y0 = ty * TH;
+      for (int Y = 0; Y < TH; ++Y) {
+        mbar_wait(&bar_rfull[Y], tile_iter & 1);
+        tc_fence_after();
+        float acc[COUT];
+        load_acc_row<COUT>(tlane + static_cast<uint32_t>(Y * COUT), acc);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_rempty[Y]);
+        const int y = y0 + Y;
+        if (y < args.H && x < args.W) epilogue_pixel<COUT, EPI>(args, s_bias, s_prelu, acc, n, y, x);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace b200sr

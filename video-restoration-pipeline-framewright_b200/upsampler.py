@@ -1,0 +1,177 @@
+"""`RealESRGANer` duck type backed by the B200 engine.
+
+The reference builds `RealESRGANer(scale, model_path, dni_weight, model, tile, tile_pad, pre_pad, half, gpu_id)`
+(`/root/reference/src/framewright/processors/pytorch_realesrgan.py:160-170`, `cli.py:742-750`,
+`face_restore.py:388-399`) and calls `.enhance(img, outscale=...) -> (output, img_mode)`
+(`pytorch_realesrgan.py:223`, `enhancement/super_resolution.py:524`, `cli.py:769`).  This class keeps that
+constructor and that call; the pre-process / tile loop / forward / post-process / uint8 conversion all
+run on the GPU inside libb200sr.so (`b200sr_upscale_host_u8`).
+
+Unlike the upstream object this one is re-entrant: `enhance` keeps no per-call state on `self` and
+serialises engine access with a lock (the reference calls it from several threads,
+`restorer.py:1894`).
+"""
+from __future__ import annotations
+
+import logging
+import os
+import threading
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .archs import MODEL_ARCHS, ArchDesc, make_synthetic_state_dict
+from .engine import B200Engine, EngineError
+
+logger = logging.getLogger(__name__)
+
+
+class ArchSpec:
+    """What the `RRDBNet(...)` / `SRVGGNetCompact(...)` shim constructors return: an architecture
+    descriptor plus an (optional) state dict -- not a torch module."""
+
+    def __init__(self, arch: ArchDesc, state_dict: Optional[Dict[str, torch.Tensor]] = None):
+        self.arch = arch
+        self._state_dict = state_dict
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
+        self._state_dict = dict(sd)
+        return self
+
+    def state_dict(self):
+        return self._state_dict
+
+    def eval(self):
+        return self
+
+    def to(self, *_a, **_k):
+        return self
+
+    def half(self):
+        return self
+
+
+def _load_checkpoint(path: str) -> Dict[str, torch.Tensor]:
+    """Upstream loader: torch.load, prefer 'params_ema', else 'params', else the dict itself."""
+    loadnet = torch.load(path, map_location="cpu")
+    if isinstance(loadnet, dict):
+        for key in ("params_ema", "params"):
+            if key in loadnet:
+                return loadnet[key]
+    return loadnet
+
+
+def _arch_for_model_path(model_path: Optional[str]) -> Optional[str]:
+    if not model_path:
+        return None
+    base = os.path.basename(str(model_path))
+    stem = base[:-4] if base.endswith(".pth") else base
+    return stem if stem in MODEL_ARCHS else None
+
+
+class RealESRGANer:
+    """Drop-in for `realesrgan.RealESRGANer` on a B200."""
+
+    def __init__(self, scale, model_path=None, dni_weight=None, model=None, tile=0, tile_pad=10, pre_pad=10,
+                 half=False, device=None, gpu_id=None, state_dict=None, model_name=None, synthetic_seed=0):
+        self.scale = int(scale)
+        self.tile_size = int(tile or 0)
+        self.tile_pad = int(tile_pad)
+        self.pre_pad = int(pre_pad)
+        self.mod_scale = None
+        self.half = bool(half)  # accepted for API parity; the engine always computes bf16-in / fp32-accumulate
+        if dni_weight is not None:
+            raise NotImplementedError("dni_weight (network interpolation) is not supported by the B200 engine")
+        if gpu_id is None:
+            gpu_id = device.index if isinstance(device, torch.device) and device.index is not None else 0
+        self.gpu_id = int(gpu_id)
+        self.device = torch.device(f"cuda:{self.gpu_id}")
+
+        name = model_name or _arch_for_model_path(model_path)
+        if isinstance(model, ArchSpec):
+            arch = model.arch
+            if state_dict is None:
+                state_dict = model.state_dict()
+        elif name is not None:
+            arch = MODEL_ARCHS[name]
+        else:
+            raise EngineError("cannot determine the architecture: pass model=<RRDBNet(...) shim> or model_name=")
+        # upstream ships realesr-general-x4v3 / realesr-animevideov3 as SRVGGNetCompact checkpoints even though
+        # the reference constructs RRDBNet for those names (SURVEY.md finding 3): the name wins.
+        if name in MODEL_ARCHS and MODEL_ARCHS[name] != arch:
+            logger.info("model name %s selects %s over the passed architecture", name, MODEL_ARCHS[name].kind)
+            arch = MODEL_ARCHS[name]
+        if arch.scale != self.scale:
+            raise EngineError(f"scale {self.scale} does not match the {arch.kind} network scale {arch.scale}")
+
+        if state_dict is None:
+            local = str(model_path) if model_path and os.path.isfile(str(model_path)) else None
+            if local is not None:
+                state_dict = _load_checkpoint(local)
+            else:
+                # Weight URLs cannot be fetched offline: deterministic synthetic weights of the same architecture.
+                if model_path:
+                    logger.warning("checkpoint %s not available locally; using synthetic weights (seed %d)",
+                                   model_path, synthetic_seed)
+                synth_name = name if name in MODEL_ARCHS else next(k for k, v in MODEL_ARCHS.items() if v == arch)
+                state_dict = make_synthetic_state_dict(synth_name, synthetic_seed)
+        self.arch = arch
+        self._engine = B200Engine(arch, state_dict, gpu_id=self.gpu_id)
+        self._lock = threading.Lock()
+
+    # --------------------------------------------------------------------------------------------
+    def _run_u8(self, img_bgr_u8: np.ndarray) -> np.ndarray:
+        with self._lock:
+            return self._engine.upscale_host(img_bgr_u8, tile=self.tile_size, tile_pad=self.tile_pad,
+                                             pre_pad=self.pre_pad)
+
+    def enhance(self, img: np.ndarray, outscale: Optional[float] = None,
+                alpha_upsampler: str = "realesrgan") -> Tuple[np.ndarray, str]:
+        """uint8 BGR / gray / BGRA ndarray -> (uint8 ndarray scaled by `outscale` or the net scale, img_mode)."""
+        import cv2
+
+        if not isinstance(img, np.ndarray) or img.ndim not in (2, 3):
+            raise EngineError("img must be an HxW or HxWxC ndarray")
+        h_input, w_input = img.shape[0:2]
+        if img.dtype != np.uint8:
+            if np.max(img) > 256:
+                raise NotImplementedError("16-bit input is not supported by the B200 uint8 engine path")
+            img = img.astype(np.uint8)
+        if img.ndim == 2:
+            img_mode = "L"
+            out = self._run_u8(cv2.cvtColor(img, cv2.COLOR_GRAY2BGR))
+            output = cv2.cvtColor(out, cv2.COLOR_BGR2GRAY)
+        elif img.shape[2] == 4:
+            img_mode = "RGBA"
+            out = self._run_u8(np.ascontiguousarray(img[:, :, 0:3]))
+            alpha = img[:, :, 3]
+            if alpha_upsampler == "realesrgan":
+                a = self._run_u8(cv2.cvtColor(alpha, cv2.COLOR_GRAY2BGR))
+                out_alpha = cv2.cvtColor(a, cv2.COLOR_BGR2GRAY)
+            else:
+                h, w = alpha.shape[0:2]
+                out_alpha = cv2.resize(alpha, (w * self.scale, h * self.scale), interpolation=cv2.INTER_LINEAR)
+            output = cv2.cvtColor(out, cv2.COLOR_BGR2BGRA)
+            output[:, :, 3] = out_alpha
+        elif img.shape[2] == 3:
+            img_mode = "RGB"
+            output = self._run_u8(np.ascontiguousarray(img))
+        else:
+            raise EngineError(f"unsupported channel count {img.shape[2]}")
+        if outscale is not None and float(outscale) != float(self.scale):
+            output = cv2.resize(output, (int(w_input * outscale), int(h_input * outscale)),
+                                interpolation=cv2.INTER_LANCZOS4)
+        return output, img_mode
+
+    def enhance_batch(self, frames: np.ndarray) -> np.ndarray:
+        """[N,H,W,3] uint8 BGR -> [N,H*s,W*s,3]; frames are independent (one launch sequence for all N)."""
+        with self._lock:
+            return self._engine.upscale_host(frames, tile=self.tile_size, tile_pad=self.tile_pad, pre_pad=self.pre_pad)
+
+    @property
+    def engine(self) -> B200Engine:
+        return self._engine
+
+    def close(self) -> None:
+        self._engine.close()
