@@ -86,11 +86,18 @@ int b200sr_last_launch_count(const b200sr_engine* e);
 /* Debug / measurement hooks (not part of the reference surface). */
 int b200sr_set_option(b200sr_engine* e, const char* key, int value);
 
+/* Per-kernel-class timing collected while option "profile" is 1 (CUDA events around every launch).
+ * Arrays of length nclass >= 10, indexed: 0 conv<32,act> 1 conv<64,act> 2 conv<64,prelu> 3 conv<64,rdb5>
+ * 4 conv<64,rdb5+rrdb> 5 conv<64,add> 6 conv<16,last_u8> 7 conv<48,srvgg_last> 8 first_conv 9 upsample2x.
+ * flops = algorithmic FLOPs (true channel counts).  Clears the collected records. */
+int b200sr_get_profile(b200sr_engine* e, int nclass, double* ms, double* flops, int* launches);
+
 /* Test hook: one tensor-core 3x3 conv layer on caller-provided device tensors (bf16 NHWC in/out,
- * fp32 OIHW host weights).  epi 0: leaky(slope) ; epi 1: PReLU(prelu_host[64]).  Synchronous. */
+ * fp32 OIHW host weights).  epi 0: leaky(slope) ; epi 1: PReLU(prelu_host[64]); fp16 != 0: tensors and
+ * weights are fp16 instead of bf16.  Synchronous. */
 int b200sr_debug_conv3x3(int device, const void* in_dev, int n, int h, int w, int in_pitch, int cin,
                          const float* weight, const float* bias, int cout, int epi, float slope,
-                         const float* prelu_host, void* out_dev, int out_pitch, int out_choff, int force_th,
+                         const float* prelu_host, void* out_dev, int out_pitch, int out_choff, int fp16, int force_th,
                          int max_ctas, void* cuda_stream, char* errbuf, int errbuf_len);
 
 const char* b200sr_last_error(const b200sr_engine* e);

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 def _ref_conv(x_bf16_nhwc, cin, weight, bias, slope=None, prelu=None):
     x = x_bf16_nhwc[..., :cin].float().permute(0, 3, 1, 2).contiguous()
-    w = weight.to(torch.bfloat16).float()
+    w = weight.to(x_bf16_nhwc.dtype).float()
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     y = F.conv2d(x.double(), w.double().to(x.device), bias.double().to(x.device), padding=1).float()
@@ -66,6 +66,26 @@ def test_conv_matches_fp32_reference(native_lib, n, h, w, pitch, cin, cout, forc
     mask = torch.ones(out_pitch, dtype=torch.bool)
     mask[choff:choff + cout] = False
     assert torch.all(out[..., mask.cuda()].float() == 7.0)
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 64), (96, 32)])
+def test_conv_fp16_format(native_lib, cin, cout):
+    """Same kernels with fp16 tensors/weights (HR tail and SRVGG layers); tolerance 2^-11 relative."""
+    from framewright_b200.engine import debug_conv3x3
+
+    g = torch.Generator().manual_seed(77 + cin)
+    n, h, w = 1, 19, 140
+    pitch = 64 if cout == 64 else 192
+    x = (torch.randn(n, h, w, pitch, generator=g) * 0.5).to(torch.float16).cuda()
+    weight = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    choff = 0 if cout == 64 else cin
+    out = torch.zeros((n, h, w, pitch), dtype=torch.float16, device="cuda")
+    debug_conv3x3(x, cin, weight, bias, out, out_choff=choff, slope=0.2)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, cin, weight, bias, slope=0.2)
+    err = (out[..., choff:choff + cout].float() - ref).abs()
+    assert torch.all(err <= ref.abs() * 2.0 ** -10 + 2e-4), float(err.max())
 
 
 def test_conv_prelu(native_lib):

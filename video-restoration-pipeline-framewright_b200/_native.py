@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "b200sr_create", "b200sr_destroy", "b200sr_num_convs", "b200sr_num_prelus", "b200sr_set_conv",
     "b200sr_set_prelu", "b200sr_finalize", "b200sr_output_dims", "b200sr_workspace_bytes",
     "b200sr_enqueue_u8", "b200sr_upscale_host_u8", "b200sr_last_launch_count", "b200sr_set_option",
-    "b200sr_last_error", "b200sr_version", "b200sr_debug_conv3x3",
+    "b200sr_last_error", "b200sr_version", "b200sr_debug_conv3x3", "b200sr_get_profile",
 ]
 
 OK, ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_STATE = 0, 1, 2, 3, 4
@@ -133,9 +133,12 @@ def load() -> ctypes.CDLL:
         lib.b200sr_version.argtypes = []
         lib.b200sr_version.restype = c_char_p
         lib.b200sr_debug_conv3x3.argtypes = [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, fp, fp, c_int, c_int,
-                                             c_float, fp, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_char_p,
-                                             c_int]
+                                             c_float, fp, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                             c_char_p, c_int]
         lib.b200sr_debug_conv3x3.restype = c_int
+        dp = ctypes.POINTER(ctypes.c_double)
+        lib.b200sr_get_profile.argtypes = [c_void_p, c_int, dp, dp, ctypes.POINTER(c_int)]
+        lib.b200sr_get_profile.restype = c_int
         _lib = lib
         return lib
 

@@ -103,7 +103,8 @@ def make_synthetic_state_dict(model_name: str, seed: int = 0) -> Dict[str, torch
 
     Recipe (committed so goldens are reproducible; SURVEY.md §7 hard part 3):
       * RDB convs: N(0, 2/fan_in) scaled by 0.1, zero bias   (upstream `default_init_weights(scale=0.1)`).
-      * every other conv: U(-b, b) with b = 1/sqrt(fan_in) for weight and bias (torch Conv2d default).
+      * every other conv: U(-b, b) with b = 1/sqrt(fan_in) for weight and bias (torch Conv2d default);
+        SRVGG body convs: N(0, 2 / (1.0625 fan_in)) weights (variance-preserving through PReLU).
       * PReLU slopes: 0.25 + U(-0.1, 0.1) per channel (torch default is a constant 0.25; jitter makes
         the per-channel path observable).
       * the last conv is re-centred so the pre-clamp output sits inside [0, 1] instead of saturating:
@@ -123,6 +124,12 @@ def make_synthetic_state_dict(model_name: str, seed: int = 0) -> Dict[str, torch
         if ".rdb" in name:
             w = torch.randn(cout, cin, 3, 3, generator=g) * math.sqrt(2.0 / fan_in) * 0.1
             b = torch.zeros(cout)
+        elif arch.kind == "srvgg" and not is_last:
+            # variance-preserving through PReLU(0.25): N(0, 2 / ((1 + 0.25^2) fan_in)); otherwise the
+            # 32-conv body decays to nothing and the output is just the nearest-upsampled input
+            bound = 1.0 / math.sqrt(fan_in)
+            w = torch.randn(cout, cin, 3, 3, generator=g) * math.sqrt(2.0 / (1.0625 * fan_in))
+            b = (torch.rand(cout, generator=g) * 2 - 1) * bound
         else:
             bound = 1.0 / math.sqrt(fan_in)
             w = (torch.rand(cout, cin, 3, 3, generator=g) * 2 - 1) * bound
@@ -139,4 +146,4 @@ def make_synthetic_state_dict(model_name: str, seed: int = 0) -> Dict[str, torch
 
 # Output-range gains for the synthetic recipe, chosen once with the fp32 oracle on uniform-noise
 # frames so the pre-clamp output has sigma ~ 0.15 (few saturated pixels); see oracle/gen_golden.py.
-LAST_GAIN = {("rrdb", 4, 23): 0.45, ("rrdb", 4, 6): 4.0, ("rrdb", 2, 23): 0.25, ("srvgg", 4, 16): 1.0, ("srvgg", 4, 32): 1.0}
+LAST_GAIN = {("rrdb", 4, 23): 0.45, ("rrdb", 4, 6): 4.0, ("rrdb", 2, 23): 0.25, ("srvgg", 4, 16): 0.35, ("srvgg", 4, 32): 0.5}

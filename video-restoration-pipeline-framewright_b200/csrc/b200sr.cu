@@ -10,6 +10,7 @@
 #include <vector>
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "../../include/b200sr.h"
@@ -25,6 +26,7 @@ struct Layer {
   int cin = 0, cout = 0;   // true channel counts
   int coutp = 0;           // tensor-core N (16 / 32 / 48 / 64)
   bool set = false;
+  bool fp16 = false;            // 16-bit format of this layer's inputs and weights (false = bf16)
   std::vector<float> w, b;      // host fp32 OIHW / bias
   uint8_t* d_wpack = nullptr;   // packed bf16 image (tensor-core layers)
   float* d_wfirst = nullptr;    // [9][cin][64] fp32 (first layer, CUDA-core kernel)
@@ -44,6 +46,13 @@ inline uint16_t f2bf(float f) {  // round-to-nearest-even, matches __float2bfloa
   if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
   u += 0x7fffu + ((u >> 16) & 1u);
   return static_cast<uint16_t>(u >> 16);
+}
+
+inline uint16_t f2h(float f) {
+  __half h = __float2half_rn(f);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
 }
 
 }  // namespace
@@ -69,6 +78,20 @@ struct b200sr_engine {
   int opt_force_th = 0;     // 0 = auto
   int opt_max_ctas = 0;     // 0 = one per SM
   bool attrs_set = false;
+  // optional per-kernel-class timing (CUDA events around every launch; option "profile")
+  int opt_profile = 0;
+  struct ProfRec {
+    int cls;
+    double flops;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+};
+
+enum ProfClass {
+  PC_CONV32_ACT = 0, PC_CONV64_ACT, PC_CONV64_PRELU, PC_CONV64_RDB5, PC_CONV64_RDB5_RRDB, PC_CONV64_ADD,
+  PC_CONV16_LAST, PC_CONV48_SRVGG_LAST, PC_FIRST, PC_UPSAMPLE, PC_COUNT
 };
 
 namespace {
@@ -77,6 +100,33 @@ int fail(b200sr_engine* e, int code, const std::string& msg) {
   if (e) e->err = msg;
   return code;
 }
+
+cudaEvent_t prof_event(b200sr_engine* e) {
+  if (!e->ev_pool.empty()) {
+    cudaEvent_t ev = e->ev_pool.back();
+    e->ev_pool.pop_back();
+    return ev;
+  }
+  cudaEvent_t ev = nullptr;
+  cudaEventCreate(&ev);
+  return ev;
+}
+struct ProfScope {
+  b200sr_engine* e;
+  cudaStream_t st;
+  size_t idx = 0;
+  bool on;
+  ProfScope(b200sr_engine* e_, int cls, double flops, cudaStream_t st_) : e(e_), st(st_), on(e_->opt_profile != 0) {
+    if (!on) return;
+    b200sr_engine::ProfRec r{cls, flops, prof_event(e), prof_event(e)};
+    cudaEventRecord(r.e0, st);
+    idx = e->prof.size();
+    e->prof.push_back(r);
+  }
+  ~ProfScope() {
+    if (on) cudaEventRecord(e->prof[idx].e1, st);
+  }
+};
 
 #define CUDA_TRY(e, expr)                                                                          \
   do {                                                                                             \
@@ -112,15 +162,19 @@ void build_layers(b200sr_engine* e) {
         for (int k = 0; k < 4; ++k) add(nf + k * gc, gc);
         add(nf + 4 * gc, nf);
       }
-    add(nf, nf);  // conv_body
+    add(nf, nf);  // conv_body (bf16 in, fp16 out)
+    // HR tail in fp16: its roundings land straight in the [0,1] image (DESIGN.md "16-bit formats")
     add(nf, nf);  // conv_up1
     add(nf, nf);  // conv_up2
     add(nf, nf);  // conv_hr
     add(nf, 3);   // conv_last
+    for (size_t i = e->layers.size() - 4; i < e->layers.size(); ++i) e->layers[i].fp16 = true;
   } else {
+    // SRVGG has no fp32 residual trunk: all 16-bit tensors are fp16
     add(3, nf);
     for (int i = 0; i < d.num_block; ++i) add(nf, nf);
     add(nf, 3 * d.scale * d.scale);
+    for (auto& l : e->layers) l.fp16 = true;
     e->prelu_host.resize(d.num_block + 1);
     e->prelu_dev.assign(d.num_block + 1, nullptr);
   }
@@ -146,7 +200,7 @@ std::vector<uint8_t> pack_weights(const Layer& l) {
             const float v = l.w[((static_cast<size_t>(co) * l.cin + ci) * 3 + ky) * 3 + dx];
             uint32_t off = static_cast<uint32_t>(r) * 128 + (j / 8) * 16 + (j % 8) * 2;
             off ^= ((off >> 7) & 7u) << 4;
-            const uint16_t h = f2bf(v);
+            const uint16_t h = l.fp16 ? f2h(v) : f2bf(v);
             memcpy(tile + off, &h, 2);
           }
         }
@@ -156,8 +210,10 @@ std::vector<uint8_t> pack_weights(const Layer& l) {
 }
 
 template <int COUT, int EPI>
-int launch_conv_inst(b200sr_engine* e, const CUtensorMap& amap, const ConvArgs& a, cudaStream_t st) {
+int launch_conv_inst(b200sr_engine* e, const CUtensorMap& amap, const ConvArgs& a, cudaStream_t st, int pcls,
+                     double flops) {
   using Cfg = ConvCfg<COUT>;
+  ProfScope prof_scope(e, pcls, flops, st);
   static bool attr_done[16] = {};
   auto kern = conv3x3_tc_kernel<COUT, EPI>;
   if (!attr_done[e->device & 15]) {
@@ -212,15 +268,18 @@ int launch_conv(b200sr_engine* e, const Layer& l, int epi, const ConvIO& io, Con
   a.ntiles = a.xtiles * a.ytiles * io.N;
   a.wpack = l.d_wpack;
   a.bias = l.d_bias;
+  a.in_fp16 = l.fp16 ? 1 : 0;
+  // algorithmic FLOPs of this launch: true channel counts, every output pixel, 9 taps
+  const double fl = 2.0 * 9.0 * l.cin * l.cout * static_cast<double>(io.N) * io.H * io.W;
   switch (l.coutp * 16 + epi) {
-    case 32 * 16 + EPI_ACT_BF16: return launch_conv_inst<32, EPI_ACT_BF16>(e, amap, a, st);
-    case 64 * 16 + EPI_ACT_BF16: return launch_conv_inst<64, EPI_ACT_BF16>(e, amap, a, st);
-    case 64 * 16 + EPI_PRELU_BF16: return launch_conv_inst<64, EPI_PRELU_BF16>(e, amap, a, st);
-    case 64 * 16 + EPI_RDB5: return launch_conv_inst<64, EPI_RDB5>(e, amap, a, st);
-    case 64 * 16 + EPI_RDB5_RRDB: return launch_conv_inst<64, EPI_RDB5_RRDB>(e, amap, a, st);
-    case 64 * 16 + EPI_ADD_F32: return launch_conv_inst<64, EPI_ADD_F32>(e, amap, a, st);
-    case 16 * 16 + EPI_LAST_U8: return launch_conv_inst<16, EPI_LAST_U8>(e, amap, a, st);
-    case 48 * 16 + EPI_SRVGG_LAST: return launch_conv_inst<48, EPI_SRVGG_LAST>(e, amap, a, st);
+    case 32 * 16 + EPI_ACT_BF16: return launch_conv_inst<32, EPI_ACT_BF16>(e, amap, a, st, PC_CONV32_ACT, fl);
+    case 64 * 16 + EPI_ACT_BF16: return launch_conv_inst<64, EPI_ACT_BF16>(e, amap, a, st, PC_CONV64_ACT, fl);
+    case 64 * 16 + EPI_PRELU_BF16: return launch_conv_inst<64, EPI_PRELU_BF16>(e, amap, a, st, PC_CONV64_PRELU, fl);
+    case 64 * 16 + EPI_RDB5: return launch_conv_inst<64, EPI_RDB5>(e, amap, a, st, PC_CONV64_RDB5, fl);
+    case 64 * 16 + EPI_RDB5_RRDB: return launch_conv_inst<64, EPI_RDB5_RRDB>(e, amap, a, st, PC_CONV64_RDB5_RRDB, fl);
+    case 64 * 16 + EPI_ADD_F32: return launch_conv_inst<64, EPI_ADD_F32>(e, amap, a, st, PC_CONV64_ADD, fl);
+    case 16 * 16 + EPI_LAST_U8: return launch_conv_inst<16, EPI_LAST_U8>(e, amap, a, st, PC_CONV16_LAST, fl);
+    case 48 * 16 + EPI_SRVGG_LAST: return launch_conv_inst<48, EPI_SRVGG_LAST>(e, amap, a, st, PC_CONV48_SRVGG_LAST, fl);
     default: return fail(e, B200SR_ERR_INVALID, "no kernel instance for this (Cout, epilogue)");
   }
 }
@@ -278,8 +337,8 @@ int ensure_ws(b200sr_engine* e, size_t bytes, cudaStream_t st) {
   return B200SR_OK;
 }
 
-int run_first(b200sr_engine* e, const Region& R, int s, int H, int W, __nv_bfloat16* out, int out_pitch, float* xa,
-              float* xb, float* f0, float* inrgb, const float* prelu, cudaStream_t st) {
+int run_first(b200sr_engine* e, const Region& R, int s, int H, int W, __nv_bfloat16* out, int out_pitch, int out_fp16,
+              float* xa, float* xb, float* f0, float* inrgb, const float* prelu, cudaStream_t st) {
   const Layer& l = e->layers[0];
   FirstArgs a{};
   a.src = R.src;
@@ -299,11 +358,13 @@ int run_first(b200sr_engine* e, const Region& R, int s, int H, int W, __nv_bfloa
   a.prelu = prelu;
   a.out = out;
   a.out_pitch = out_pitch;
+  a.out_fp16 = out_fp16;
   a.xa = xa;
   a.xb = xb;
   a.f0 = f0;
   a.inrgb = inrgb;
   dim3 grid((W + 127) / 128, H, R.n);
+  ProfScope prof_scope(e, PC_FIRST, 2.0 * 9.0 * l.cin * 64 * static_cast<double>(R.n) * H * W, st);
   if (l.cin == 3) {
     const size_t sm = 9 * 3 * 64 * sizeof(float);
     first_conv_kernel<3><<<grid, 128, sm, st>>>(a);
@@ -319,6 +380,7 @@ int run_first(b200sr_engine* e, const Region& R, int s, int H, int W, __nv_bfloa
 int run_upsample(b200sr_engine* e, const void* in, void* out, int N, int H, int W, cudaStream_t st) {
   const size_t total = static_cast<size_t>(N) * 2 * H * 2 * W * 8;
   const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(e->num_sms) * 16));
+  ProfScope prof_scope(e, PC_UPSAMPLE, 0.0, st);
   upsample2x_kernel<<<grid, 256, 0, st>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), N, H, W);
   CUDA_TRY(e, cudaGetLastError());
   e->launches++;
@@ -365,7 +427,7 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
     __nv_bfloat16* U3 = reinterpret_cast<__nv_bfloat16*>(take(px * 16 * 64 * 2));
     __nv_bfloat16* U4 = reinterpret_cast<__nv_bfloat16*>(take(px * 16 * 64 * 2));
 
-    rc = run_first(e, R, s, H, W, D[0], 192, xa, xb, f0, nullptr, nullptr, st);
+    rc = run_first(e, R, s, H, W, D[0], 192, 0, xa, xb, f0, nullptr, nullptr, st);
     if (rc) return rc;
     int li = 1, cur_d = 0;
     for (int b = 0; b < d.num_block; ++b)
@@ -395,6 +457,7 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
       ConvArgs a = base;
       a.out = U0;
       a.out_pitch = 64;
+      a.out_fp16 = 1;
       a.fadd = f0;
       rc = launch_conv(e, e->layers[li++], EPI_ADD_F32, io, a, st);
       if (rc) return rc;
@@ -407,6 +470,7 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
       a.slope = 0.2f;
       a.out = U2;
       a.out_pitch = 64;
+      a.out_fp16 = 1;
       rc = launch_conv(e, e->layers[li++], EPI_ACT_BF16, io, a, st);
       if (rc) return rc;
     }
@@ -418,6 +482,7 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
       a.slope = 0.2f;
       a.out = U4;
       a.out_pitch = 64;
+      a.out_fp16 = 1;
       rc = launch_conv(e, e->layers[li++], EPI_ACT_BF16, io, a, st);
       if (rc) return rc;
     }
@@ -427,6 +492,7 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
       a.slope = 0.2f;
       a.out = U3;
       a.out_pitch = 64;
+      a.out_fp16 = 1;
       rc = launch_conv(e, e->layers[li++], EPI_ACT_BF16, io, a, st);
       if (rc) return rc;
     }
@@ -440,7 +506,7 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
     S[0] = reinterpret_cast<__nv_bfloat16*>(take(px * 64 * 2));
     S[1] = reinterpret_cast<__nv_bfloat16*>(take(px * 64 * 2));
     float* inrgb = reinterpret_cast<float*>(take(px * 4 * 4));
-    rc = run_first(e, R, 1, H, W, S[0], 64, nullptr, nullptr, nullptr, inrgb, e->prelu_dev[0], st);
+    rc = run_first(e, R, 1, H, W, S[0], 64, 1, nullptr, nullptr, nullptr, inrgb, e->prelu_dev[0], st);
     if (rc) return rc;
     int cur_s = 0;
     for (int i = 0; i < d.num_block; ++i) {
@@ -448,6 +514,7 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
       ConvArgs a = base;
       a.out = S[cur_s ^ 1];
       a.out_pitch = 64;
+      a.out_fp16 = 1;
       a.prelu = e->prelu_dev[i + 1];
       rc = launch_conv(e, e->layers[1 + i], EPI_PRELU_BF16, io, a, st);
       if (rc) return rc;
@@ -518,6 +585,11 @@ void b200sr_destroy(b200sr_engine* e) {
   if (e->stage_in) cudaFree(e->stage_in);
   if (e->stage_out) cudaFree(e->stage_out);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  for (auto& r : e->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   delete e;
 }
 
@@ -715,7 +787,32 @@ int b200sr_set_option(b200sr_engine* e, const char* key, int value) {
     e->opt_max_ctas = value;
     return B200SR_OK;
   }
+  if (!strcmp(key, "profile")) {  // 1: time every launch with CUDA events; read back with b200sr_get_profile
+    e->opt_profile = value;
+    return B200SR_OK;
+  }
   return fail(e, B200SR_ERR_INVALID, std::string("unknown option ") + key);
+}
+
+int b200sr_get_profile(b200sr_engine* e, int nclass, double* ms, double* flops, int* launches) {
+  if (!e || !ms || !flops || !launches || nclass < PC_COUNT) return B200SR_ERR_INVALID;
+  for (int i = 0; i < nclass; ++i) {
+    ms[i] = 0;
+    flops[i] = 0;
+    launches[i] = 0;
+  }
+  for (auto& r : e->prof) {
+    cudaEventSynchronize(r.e1);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    ms[r.cls] += t;
+    flops[r.cls] += r.flops;
+    launches[r.cls] += 1;
+    e->ev_pool.push_back(r.e0);
+    e->ev_pool.push_back(r.e1);
+  }
+  e->prof.clear();
+  return B200SR_OK;
 }
 
 // ---- test hook: one tensor-core conv layer on caller-provided device tensors -------------------
@@ -723,7 +820,7 @@ int b200sr_set_option(b200sr_engine* e, const char* key, int value) {
 // epi: 0 = leaky(slope) -> bf16 slice ; 1 = prelu(prelu_host) -> bf16.
 int b200sr_debug_conv3x3(int device, const void* in_dev, int n, int h, int w, int in_pitch, int cin,
                          const float* weight, const float* bias, int cout, int epi, float slope,
-                         const float* prelu_host, void* out_dev, int out_pitch, int out_choff, int force_th,
+                         const float* prelu_host, void* out_dev, int out_pitch, int out_choff, int fp16, int force_th,
                          int max_ctas, void* cuda_stream, char* errbuf, int errbuf_len) {
   b200sr_engine e;
   e.device = device;
@@ -744,6 +841,7 @@ int b200sr_debug_conv3x3(int device, const void* in_dev, int n, int h, int w, in
   l.cin = cin;
   l.cout = cout;
   l.coutp = coutp_for(cout);
+  l.fp16 = fp16 != 0;
   if (!((l.coutp == 32 && epi == 0) || (l.coutp == 64 && (epi == 0 || epi == 1))))
     return report(fail(&e, B200SR_ERR_INVALID, "debug conv supports Cout 32 (leaky) and 64 (leaky / prelu)"));
   l.w.assign(weight, weight + static_cast<size_t>(cout) * cin * 9);
@@ -764,6 +862,7 @@ int b200sr_debug_conv3x3(int device, const void* in_dev, int n, int h, int w, in
     a.out = static_cast<__nv_bfloat16*>(out_dev);
     a.out_pitch = out_pitch;
     a.out_choff = out_choff;
+    a.out_fp16 = fp16 ? 1 : 0;
     if (epi == 1) {
       if (!prelu_host) return fail(&e, B200SR_ERR_INVALID, "prelu slopes missing");
       CUDA_TRY(&e, cudaMalloc(&d_prelu, 64 * 4));

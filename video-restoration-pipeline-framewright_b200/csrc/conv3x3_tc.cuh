@@ -29,6 +29,7 @@
 //     epilogue (TMEM -> registers -> fused pointwise -> global).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "ptx.cuh"
 
 namespace b200sr {
@@ -53,7 +54,9 @@ struct ConvArgs {
   const float* bias;      // COUT floats
   const float* prelu;     // COUT floats (EPI_PRELU_BF16)
   float slope;            // leaky slope (EPI_ACT_BF16)
-  __nv_bfloat16* out;     // bf16 NHWC destination
+  int in_fp16;            // A (activations) and B (weights) are fp16 instead of bf16
+  int out_fp16;           // 16-bit output tensor is fp16 instead of bf16
+  __nv_bfloat16* out;     // 16-bit NHWC destination (bf16 or fp16 per out_fp16)
   int out_pitch;          // channels per pixel in `out`
   int out_choff;          // first channel written
   float* xa;              // fp32 trunk (RDB input / output, in place)
@@ -92,6 +95,10 @@ __device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&v)[8]) {
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ uint8_t quant_u8(float v) {
@@ -137,12 +144,17 @@ __device__ __forceinline__ void load_acc_row(uint32_t taddr, float (&acc)[COUT])
 }
 
 template <int COUT>
-__device__ __forceinline__ void store_bf16_row(__nv_bfloat16* dst, const float (&v)[COUT]) {
+__device__ __forceinline__ void store_bf16_row(__nv_bfloat16* dst, const float (&v)[COUT], int fp16 = 0) {
 #pragma unroll
   for (int g = 0; g < COUT / 16; ++g) {
     uint32_t p[8];
+    if (fp16) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) p[i] = pack_bf16x2(v[g * 16 + 2 * i], v[g * 16 + 2 * i + 1]);
+      for (int i = 0; i < 8; ++i) p[i] = pack_f16x2(v[g * 16 + 2 * i], v[g * 16 + 2 * i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) p[i] = pack_bf16x2(v[g * 16 + 2 * i], v[g * 16 + 2 * i + 1]);
+    }
     st_global_256(dst + g * 16, p);
   }
 }
@@ -158,14 +170,14 @@ __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* s
       float v = acc[c] + s_bias[c];
       acc[c] = v > 0.f ? v : v * a.slope;
     }
-    store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc);
+    store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc, a.out_fp16);
   } else if constexpr (EPI == EPI_PRELU_BF16) {
 #pragma unroll
     for (int c = 0; c < COUT; ++c) {
       float v = acc[c] + s_bias[c];
       acc[c] = v > 0.f ? v : v * s_prelu[c];
     }
-    store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc);
+    store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc, a.out_fp16);
   } else if constexpr (EPI == EPI_RDB5 || EPI == EPI_RDB5_RRDB) {
     float* xa = a.xa + pix * COUT;
     float* xb = a.xb + pix * COUT;
@@ -195,7 +207,7 @@ __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* s
       }
       st_global_256(xa + g * 8, o);
     }
-    store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc);
+    store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc, a.out_fp16);
   } else if constexpr (EPI == EPI_ADD_F32) {
     const float* f = a.fadd + pix * COUT;
 #pragma unroll
@@ -205,7 +217,7 @@ __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* s
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[g * 8 + i] = acc[g * 8 + i] + s_bias[g * 8 + i] + __uint_as_float(r[i]);
     }
-    store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc);
+    store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc, a.out_fp16);
   } else if constexpr (EPI == EPI_LAST_U8) {
     const int cy = y - a.crop_y0, cx = x - a.crop_x0;
     if (cy >= 0 && cy < a.crop_h && cx >= 0 && cx < a.crop_w) {
@@ -324,9 +336,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc1 = make_idesc_bf16(128, COUT);
-      const uint32_t idesc2 = make_idesc_bf16(128, 2 * COUT);
-      const uint32_t idesc3 = make_idesc_bf16(128, 3 * COUT);
+      const bool f16 = args.in_fp16 != 0;
+      const uint32_t idesc1 = make_idesc_16(128, COUT, f16);
+      const uint32_t idesc2 = make_idesc_16(128, 2 * COUT, f16);
+      const uint32_t idesc3 = make_idesc_16(128, 3 * COUT, f16);
       const uint64_t adesc0 = make_smem_desc(smem_u32(sA), 1024, SWZ_128B, 0);
       const uint64_t bdesc0 = make_smem_desc(smem_u32(sW), 1024, SWZ_128B, 0);
       int stage = 0, phase = 0, wb = 0, wphase = 0;

@@ -20,8 +20,9 @@ struct FirstArgs {
   const float* w;       // [9 taps][cin][64]
   const float* bias;    // [64]
   const float* prelu;   // [64] or nullptr
-  __nv_bfloat16* out;   // bf16 NHWC
+  __nv_bfloat16* out;   // 16-bit NHWC (bf16, or fp16 when out_fp16)
   int out_pitch;
+  int out_fp16;
   float* xa;            // optional fp32 copies of the result ([N][H][W][64])
   float* xb;
   float* f0;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(128) first_conv_kernel(const FirstArgs a) {
     for (int c = 0; c < 64; ++c) acc[c] = acc[c] > 0.f ? acc[c] : acc[c] * s_p[c];
   }
   const size_t pix = (static_cast<size_t>(n) * a.H + y) * a.W + x;
-  store_bf16_row<64>(a.out + pix * a.out_pitch, acc);
+  store_bf16_row<64>(a.out + pix * a.out_pitch, acc, a.out_fp16);
   float* f32dst[3] = {a.xa, a.xb, a.f0};
 #pragma unroll
   for (int k = 0; k < 3; ++k) {

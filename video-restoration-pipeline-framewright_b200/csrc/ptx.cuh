@@ -152,13 +152,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
   return d;
 }
 
-// Instruction descriptor: bf16 x bf16 -> fp32, A and B K-major, dense.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
-  return (1u << 4)            // D format fp32
-         | (1u << 7)          // A format bf16
-         | (1u << 10)         // B format bf16
-         | ((N >> 3) << 17)   // N / 8
-         | ((M >> 4) << 24);  // M / 16
+// Instruction descriptor (kind::f16): 16-bit A and B (both bf16, or both fp16) -> fp32, K-major, dense.
+__host__ __device__ constexpr uint32_t make_idesc_16(uint32_t M, uint32_t N, bool fp16) {
+  return (1u << 4)                    // D format fp32
+         | ((fp16 ? 0u : 1u) << 7)    // A format: 0 = fp16, 1 = bf16
+         | ((fp16 ? 0u : 1u) << 10)   // B format
+         | ((N >> 3) << 17)           // N / 8
+         | ((M >> 4) << 24);          // M / 16
 }
+__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) { return make_idesc_16(M, N, false); }
 
 }  // namespace b200sr

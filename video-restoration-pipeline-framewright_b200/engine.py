@@ -133,6 +133,19 @@ class B200Engine:
         self._check(rc, "upscale_host_u8")
         return out[0] if single else out
 
+    PROFILE_CLASSES = ["conv32_act", "conv64_act", "conv64_prelu", "conv64_rdb5", "conv64_rdb5_rrdb", "conv64_add",
+                       "conv16_last_u8", "conv48_srvgg_last", "first_conv", "upsample2x"]
+
+    def get_profile(self) -> Dict[str, Dict[str, float]]:
+        """Per-kernel-class {ms, flops, launches} collected since the last call (needs set_option('profile', 1))."""
+        n = len(self.PROFILE_CLASSES)
+        ms = (ctypes.c_double * n)()
+        fl = (ctypes.c_double * n)()
+        cnt = (ctypes.c_int * n)()
+        self._check(self._lib.b200sr_get_profile(self._h, n, ms, fl, cnt), "get_profile")
+        return {k: {"ms": ms[i], "flops": fl[i], "launches": cnt[i]} for i, k in enumerate(self.PROFILE_CLASSES)
+                if cnt[i] > 0}
+
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:
             self._lib.b200sr_destroy(self._h)
@@ -159,6 +172,7 @@ def debug_conv3x3(x_nhwc_bf16: torch.Tensor, cin: int, weight: torch.Tensor, bia
     rc = lib.b200sr_debug_conv3x3(
         x_nhwc_bf16.device.index, x_nhwc_bf16.data_ptr(), n, h, w, in_pitch, cin, _fptr(wt), _fptr(bs), wt.shape[0],
         1 if pr is not None else 0, float(slope), _fptr(pr) if pr is not None else None, out.data_ptr(),
-        out.shape[-1], out_choff, force_th, max_ctas, ctypes.c_void_p(stream), err, 512)
+        out.shape[-1], out_choff, 1 if x_nhwc_bf16.dtype == torch.float16 else 0, force_th, max_ctas,
+        ctypes.c_void_p(stream), err, 512)
     if rc != _native.OK:
         raise EngineError(f"debug_conv3x3 failed ({rc}): {err.value.decode()}")
