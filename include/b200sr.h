@@ -92,6 +92,17 @@ int b200sr_set_option(b200sr_engine* e, const char* key, int value);
  * flops = algorithmic FLOPs (true channel counts).  Clears the collected records. */
 int b200sr_get_profile(b200sr_engine* e, int nclass, double* ms, double* flops, int* launches);
 
+/* Host-only test hooks (no GPU needed).
+ * plan_regions: the regions one enhance call is split into (tile == 0: one region; else upstream
+ *   tile_process geometry); 10 ints per region: oy ox rh rw crop_y0 crop_x0 crop_h crop_w dst_y0 dst_x0.
+ *   Returns the region count (may exceed max_regions), -1 on bad arguments.
+ * pack_weights: the tensor-core weight image of one layer; returns its size in bytes.
+ * choose_th: output rows per CTA tile the launcher picks. */
+int b200sr_debug_plan_regions(int arch, int scale, int h, int w, int tile, int tile_pad, int pre_pad, int* out,
+                              int max_regions);
+long long b200sr_debug_pack_weights(const float* weight, int cout, int cin, int fp16, uint8_t* out, long long out_bytes);
+int b200sr_debug_choose_th(int coutp, int n, int h, int w, int num_sms);
+
 /* Test hook: one tensor-core 3x3 conv layer on caller-provided device tensors (bf16 NHWC in/out,
  * fp32 OIHW host weights).  epi 0: leaky(slope) ; epi 1: PReLU(prelu_host[64]); fp16 != 0: tensors and
  * weights are fp16 instead of bf16.  Synchronous. */

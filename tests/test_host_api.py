@@ -1,0 +1,244 @@
+"""Host-side mirror of the reference upscale processor API (no GPU).  The first block restates, against the
+B200 module, the live tests of /root/reference/tests/test_processors/test_pytorch_realesrgan.py (:59-116, :230-237)
+and re-implements the ones the reference cannot run (fixtures `mock_torch`/`mock_cv2` are never registered there)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import framewright_b200  # noqa: F401
+from framewright_b200 import multi_gpu as mg
+from framewright_b200 import pytorch_realesrgan as pr
+from framewright_b200 import super_resolution as srm
+
+
+# ---- PyTorchESRGANConfig (reference tests :59-116) -------------------------------------------------
+def test_config_defaults():
+    c = pr.PyTorchESRGANConfig()
+    assert (c.model_name, c.scale_factor, c.tile_size, c.tile_pad, c.pre_pad, c.half_precision, c.gpu_id) == (
+        "RealESRGAN_x4plus", 4, 0, 10, 0, True, 0)
+
+
+@pytest.mark.parametrize("name", ["RealESRGAN_x4plus", "RealESRGAN_x4plus_anime_6B", "RealESRGAN_x2plus",
+                                  "realesr-animevideov3", "realesr-general-x4v3"])
+def test_config_valid_models(name):
+    pr.PyTorchESRGANConfig(model_name=name).validate()
+
+
+def test_config_invalid_model():
+    with pytest.raises(ValueError, match="Invalid model"):
+        pr.PyTorchESRGANConfig(model_name="nope").validate()
+
+
+@pytest.mark.parametrize("scale", [1, 3, 8])
+def test_config_invalid_scale(scale):
+    with pytest.raises(ValueError, match="Scale factor must be 2 or 4"):
+        pr.PyTorchESRGANConfig(scale_factor=scale).validate()
+
+
+# ---- name map (reference tests :230-237) -------------------------------------------------------------
+def test_ncnn_name_map():
+    assert pr.convert_ncnn_model_name("realesrgan-x4plus") == "RealESRGAN_x4plus"
+    assert pr.convert_ncnn_model_name("realesrgan-x4plus-anime") == "RealESRGAN_x4plus_anime_6B"
+    assert pr.convert_ncnn_model_name("realesr-animevideov3") == "realesr-animevideov3"
+    assert pr.convert_ncnn_model_name("realesrnet-x4plus") == "realesr-general-x4v3"
+    assert pr.convert_ncnn_model_name("realesrgan-x2plus") == "RealESRGAN_x2plus"
+    assert pr.convert_ncnn_model_name("unknown-model") == "RealESRGAN_x4plus"
+    assert set(pr.NCNN_TO_PYTORCH_MODEL.values()) == set(pr.VALID_MODELS)
+
+
+# ---- availability / error convention ---------------------------------------------------------------
+def test_availability_is_memoised(monkeypatch):
+    monkeypatch.setattr(pr, "_PYTORCH_ESRGAN_AVAILABLE", True)
+    assert pr.is_pytorch_esrgan_available() is True
+    monkeypatch.setattr(pr, "_PYTORCH_ESRGAN_AVAILABLE", False)
+    assert pr.is_pytorch_esrgan_available() is False
+
+
+def test_get_upsampler_raises_without_engine(monkeypatch):
+    monkeypatch.setattr(pr, "_PYTORCH_ESRGAN_AVAILABLE", False)
+    with pytest.raises(RuntimeError, match="not available"):
+        pr.get_upsampler(pr.PyTorchESRGANConfig())
+
+
+def test_enhance_frame_never_raises_unreadable_input(tmp_path):
+    ok, err = pr.enhance_frame_pytorch(tmp_path / "missing.png", tmp_path / "out.png", pr.PyTorchESRGANConfig())
+    assert ok is False and err.startswith("Failed to read image:")
+
+
+def test_enhance_frame_reports_invalid_config(tmp_path):
+    ok, err = pr.enhance_frame_pytorch(tmp_path / "x.png", tmp_path / "o.png", pr.PyTorchESRGANConfig(model_name="bad"))
+    assert ok is False and "Invalid model" in err
+
+
+class _FakeUpsampler:
+    def __init__(self, exc=None):
+        self.exc = exc
+        self.calls = 0
+
+    def enhance(self, img, outscale=None):
+        self.calls += 1
+        if self.exc:
+            raise self.exc
+        return np.zeros((img.shape[0] * 4, img.shape[1] * 4, 3), np.uint8), "RGB"
+
+    def close(self):
+        pass
+
+
+def _write_png(path, h=8, w=8):
+    import cv2
+
+    cv2.imwrite(str(path), np.full((h, w, 3), 127, np.uint8))
+
+
+def test_enhance_frame_success_writes_output(tmp_path, monkeypatch):
+    up = _FakeUpsampler()
+    monkeypatch.setattr(pr, "get_upsampler", lambda cfg: up)
+    monkeypatch.setattr(pr, "_available_vram_mb", lambda gpu: 50000.0)
+    _write_png(tmp_path / "in.png")
+    ok, err = pr.enhance_frame_pytorch(tmp_path / "in.png", tmp_path / "out.png", pr.PyTorchESRGANConfig())
+    assert (ok, err) == (True, None) and (tmp_path / "out.png").exists() and up.calls == 1
+
+
+def test_enhance_frame_oom_message(tmp_path, monkeypatch):
+    """OOM -> (False, 'GPU out of memory: ...Try: 1) Reduce tile_size...'): callers grep for 'memory' to shrink
+    tiles (reference restorer.py:1746; intended behaviour of reference test :182-201)."""
+    from framewright_b200.engine import EngineOutOfMemory
+
+    monkeypatch.setattr(pr, "get_upsampler", lambda cfg: _FakeUpsampler(EngineOutOfMemory("GPU out of memory: 4 GiB")))
+    monkeypatch.setattr(pr, "_available_vram_mb", lambda gpu: 50000.0)
+    _write_png(tmp_path / "in.png")
+    ok, err = pr.enhance_frame_pytorch(tmp_path / "in.png", tmp_path / "out.png", pr.PyTorchESRGANConfig())
+    assert ok is False and err.startswith("GPU out of memory") and "Reduce tile_size" in err and "memory" in err
+
+
+@pytest.mark.parametrize("avail,want", [(9000.0, 0), (5000.0, 512), (3000.0, 384), (1000.0, 256)])
+def test_auto_tile_mutates_config(tmp_path, monkeypatch, avail, want):
+    """Auto mode (tile_size == 0) picks the tile from free VRAM and mutates the config like the reference
+    (:203-218; intended behaviour of reference tests :256-306: > 8000 MB -> 0, 2000-4000 MB -> 384)."""
+    monkeypatch.setattr(pr, "get_upsampler", lambda cfg: _FakeUpsampler())
+    monkeypatch.setattr(pr, "_available_vram_mb", lambda gpu: avail)
+    _write_png(tmp_path / "in.png")
+    cfg = pr.PyTorchESRGANConfig(tile_size=0)
+    ok, _ = pr.enhance_frame_pytorch(tmp_path / "in.png", tmp_path / "out.png", cfg)
+    assert ok and cfg.tile_size == want
+
+
+def test_clear_cache_is_idempotent():
+    pr.clear_upsampler_cache()
+    pr.clear_upsampler_cache()
+    assert pr._UPSAMPLER is None
+
+
+# ---- SRBackend mirror ------------------------------------------------------------------------------
+def test_sr_backend_names_scales_and_quirk():
+    b = srm.B200RealESRGANBackend(srm.SRConfig(scale=4), None, "x4plus")
+    assert b.name == "realesrgan_x4plus" and b.supported_scales == [4]
+    b2 = srm.B200RealESRGANBackend(srm.SRConfig(scale=2), None, "x2plus")
+    assert b2.supported_scales == [2] and b2._get_model_name() == "RealESRGAN_x2plus"
+    # reference quirk: variant "x2" is not in the map -> silently RealESRGAN_x4plus
+    assert srm.B200RealESRGANBackend(model_variant="x2")._get_model_name() == "RealESRGAN_x4plus"
+    assert srm.B200RealESRGANBackend(model_variant="general")._get_model_name() == "realesr-general-x4v3"
+
+
+def test_sr_backend_vram_estimate_formula():
+    b = srm.B200RealESRGANBackend()
+    assert b.estimate_vram_usage(1280, 720, 4) == 2000 + (1280 * 720 * 3 * 4 * 17) // (1024 * 1024)
+    assert srm.B200RealESRGANBackend(model_variant="anime").estimate_vram_usage(64, 64, 4) == 1500
+
+
+def test_sr_config_validation():
+    with pytest.raises(ValueError):
+        srm.SRConfig(scale=3)
+    with pytest.raises(ValueError):
+        srm.SRConfig(quality_preset="ultra")
+
+
+def test_sr_backend_dir_api_collects_failures(tmp_path, monkeypatch):
+    """frames-dir in/out: sorted *.png, same names, failures -> warnings 'Frame <name>: <err>', never raises."""
+    (tmp_path / "in").mkdir()
+    for i in range(3):
+        _write_png(tmp_path / "in" / f"frame_{i:08d}.png")
+    calls = []
+
+    def fake(inp, outp, cfg):
+        calls.append(Path(inp).name)
+        if "00000001" in str(inp):
+            return False, "boom"
+        Path(outp).write_bytes(b"x")
+        return True, None
+
+    monkeypatch.setattr(srm, "enhance_frame_pytorch", fake)
+    prog = []
+    res = srm.B200RealESRGANBackend().upscale_frames(tmp_path / "in", tmp_path / "out", 4, prog.append)
+    assert calls == sorted(calls) and len(calls) == 3
+    assert (res.frames_processed, res.frames_failed) == (2, 1)
+    assert res.warnings == ["Frame frame_00000001.png: boom"]
+    assert prog[-1] == 1.0 and res.output_dir == tmp_path / "out" and res.backend_used == "realesrgan_x4plus"
+    empty = srm.B200RealESRGANBackend().upscale_frames(tmp_path / "none", tmp_path / "out2", 4)
+    assert empty.warnings == ["No frames found"]
+
+
+# ---- frame scheduler (reference tests/test_multi_gpu.py:510-554 restated) -------------------------------
+def _gpus(n, free=None, util=None):
+    return [mg.GPUInfo(i, f"GPU{i}", 180000, (free or [180000] * n)[i], (util or [0.0] * n)[i]) for i in range(n)]
+
+
+def test_assign_round_robin_and_least_loaded():
+    frames = [Path(f"f{i}.png") for i in range(10)]
+    a = mg.assign_frames(frames, _gpus(2), mg.LoadBalanceStrategy.ROUND_ROBIN)
+    assert len(a[0]) == 5 and len(a[1]) == 5 and a[0][0] == frames[0] and a[1][0] == frames[1]
+    a = mg.assign_frames(frames, _gpus(2, util=[90.0, 10.0]), mg.LoadBalanceStrategy.LEAST_LOADED)
+    assert a[1][0] == frames[0]
+
+
+def test_assign_vram_aware_and_weighted_cover_all_frames():
+    frames = [Path(f"f{i}.png") for i in range(11)]
+    for strat in (mg.LoadBalanceStrategy.VRAM_AWARE, mg.LoadBalanceStrategy.WEIGHTED):
+        a = mg.assign_frames(frames, _gpus(3, free=[90000, 45000, 45000]), strat)
+        got = sorted(f for v in a.values() for f in v)
+        assert got == sorted(frames)
+        assert len(a[0]) >= len(a[1])
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 2000, 2001):
+        for g in (1, 2, 4, 8):
+            spans = [mg.shard_range(n, g, r) for r in range(g)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(g - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert mg.shard_range(2000, 8, 3) == (750, 1000)
+
+
+def test_gpu_health_and_result_summary():
+    assert not mg.GPUInfo(0, "x", 1, 1, 0.0, temperature_c=95.0).is_healthy
+    assert mg.GPUInfo(0, "x", 1, 1, 0.0, temperature_c=90.0).is_healthy
+    r = mg.DistributionResult(frames_per_gpu={0: [Path("a")], 1: []}, errors={"b": "x"})
+    assert r.total_frames == 1 and r.success_rate == 50.0 and "GPU0: 1" in r.summary()
+
+
+def test_distributor_empty_and_no_gpus():
+    d = mg.MultiGPUDistributor(gpus=[])
+    assert d.distribute_frames([], None, Path(".")).total_frames == 0
+    res = d.distribute_frames([Path("a.png")], lambda *a: (None, True, None), Path("."))
+    assert res.errors == {"a.png": "No GPUs available"}
+
+
+def test_distributor_process_fn_retry_on_other_gpu(tmp_path):
+    frames = [tmp_path / f"f{i}.png" for i in range(6)]
+    seen = []
+
+    def fn(inp, outdir, gpu):
+        seen.append((inp.name, gpu))
+        if gpu == 0 and inp.name == "f2.png":
+            return None, False, "gpu0 failed"
+        return outdir / inp.name, True, None
+
+    d = mg.MultiGPUDistributor(gpus=_gpus(2), strategy=mg.LoadBalanceStrategy.ROUND_ROBIN)
+    res = d.distribute_frames(frames, fn, tmp_path / "out")
+    assert res.total_frames == 6 and not res.errors
+    assert ("f2.png", 0) in seen and ("f2.png", 1) in seen and frames[2] in res.retried_frames
+    assert res.speedup_factor > 1.0

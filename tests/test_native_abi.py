@@ -1,0 +1,135 @@
+"""The C-ABI library builds for sm_100a without a GPU, loads, and exports every symbol include/b200sr.h declares.
+Host-only logic behind the ABI (tile planning, weight packing, tile-height choice) is checked against numpy /
+oracle restatements.  No compute calls here (no GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "b200sr.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200sr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported(native_lib):
+    from framewright_b200 import _native
+
+    syms = _header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(native_lib, s), f"{s} declared in include/b200sr.h but not exported"
+    assert sorted(_native.EXPORTED_SYMBOLS) == syms
+    assert b"sm_100a" in native_lib.b200sr_version()
+
+
+def test_library_is_sm100a_tcgen05(native_lib):
+    """The built library carries sm_100a SASS with tcgen05 (UTC*MMA), TMEM loads (LDTM) and TMA (UTMALDG)."""
+    import shutil
+    import subprocess
+
+    from framewright_b200 import _native
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UBLKCP"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA.16816" not in sass  # no legacy mma.sync path
+
+
+def test_create_fails_loudly_without_gpu(native_lib):
+    from framewright_b200 import _native
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    desc = _native.ModelDesc(_native.ARCH_RRDB, 4, 64, 23, 32)
+    h = ctypes.c_void_p()
+    assert native_lib.b200sr_create(ctypes.byref(desc), 0, ctypes.byref(h)) == _native.ERR_CUDA
+    assert not h.value
+
+
+@pytest.mark.parametrize("arch,scale,h,w,tile,tile_pad,pre_pad", [
+    (0, 4, 720, 1280, 512, 10, 0), (0, 4, 720, 1280, 512, 10, 10), (0, 2, 1080, 1920, 400, 10, 0),
+    (0, 2, 51, 77, 32, 4, 0), (1, 4, 100, 90, 64, 10, 10), (0, 4, 64, 64, 0, 10, 0), (0, 2, 45, 63, 0, 10, 3),
+])
+def test_plan_regions_matches_upstream_tile_process(native_lib, arch, scale, h, w, tile, tile_pad, pre_pad):
+    """Region list == the upstream tile loop's slices (oracle/oracle.py::tile_process), including the final
+    post_process crop of pre_pad / mod_pad."""
+    import math
+
+    buf = (ctypes.c_int * (10 * 64))()
+    n = native_lib.b200sr_debug_plan_regions(arch, scale, h, w, tile, tile_pad, pre_pad, buf, 64)
+    got = [tuple(buf[i * 10:(i + 1) * 10]) for i in range(n)]
+    mod = 2 if (arch == 0 and scale == 2) else 1
+    Hp = -(-(h + pre_pad) // mod) * mod
+    Wp = -(-(w + pre_pad) // mod) * mod
+    want = []
+    if tile == 0:
+        want.append((0, 0, Hp, Wp, 0, 0, h * scale, w * scale, 0, 0))
+    else:
+        for y in range(math.ceil(Hp / tile)):
+            for x in range(math.ceil(Wp / tile)):
+                x0, y0 = x * tile, y * tile
+                x1, y1 = min(x0 + tile, Wp), min(y0 + tile, Hp)
+                px0, px1 = max(x0 - tile_pad, 0), min(x1 + tile_pad, Wp)
+                py0, py1 = max(y0 - tile_pad, 0), min(y1 + tile_pad, Hp)
+                ch = min((y1 - y0) * scale, h * scale - y0 * scale)
+                cw = min((x1 - x0) * scale, w * scale - x0 * scale)
+                if ch <= 0 or cw <= 0:
+                    continue
+                want.append((py0, px0, py1 - py0, px1 - px0, (y0 - py0) * scale, (x0 - px0) * scale, ch, cw,
+                             y0 * scale, x0 * scale))
+    assert got == want
+    # the kept windows tile the destination frame exactly once
+    cover = np.zeros((h * scale, w * scale), np.int32)
+    for r in got:
+        cover[r[8]:r[8] + r[6], r[9]:r[9] + r[7]] += 1
+    assert cover.min() == 1 and cover.max() == 1
+
+
+@pytest.mark.parametrize("cout,cin,fp16", [(32, 64, 0), (32, 96, 0), (64, 192, 0), (3, 64, 1), (48, 64, 1), (64, 64, 1)])
+def test_pack_weights_layout(native_lib, cout, cin, fp16):
+    """Packed image == numpy restatement: [chunk][dx][blk*COUTP+co][64 ch], 128 B rows, 16 B chunks XOR (row & 7),
+    blk <-> ky = 2 - blk, dx <-> kx; bf16/fp16 round-to-nearest-even; zero padding of channels and rows."""
+    g = torch.Generator().manual_seed(cout * 1000 + cin)
+    w = torch.randn(cout, cin, 3, 3, generator=g)
+    wc = w.contiguous()
+    nbytes = native_lib.b200sr_debug_pack_weights(ctypes.cast(wc.data_ptr(), ctypes.POINTER(ctypes.c_float)), cout,
+                                                  cin, fp16, None, 0)
+    coutp = 16 if cout <= 16 else 32 if cout <= 32 else 48 if cout <= 48 else 64
+    nchunks = (cin + 63) // 64
+    assert nbytes == nchunks * 9 * coutp * 128
+    out = np.zeros(nbytes, np.uint8)
+    native_lib.b200sr_debug_pack_weights(ctypes.cast(wc.data_ptr(), ctypes.POINTER(ctypes.c_float)), cout, cin, fp16,
+                                         out.ctypes.data_as(ctypes.c_void_p), nbytes)
+    w16 = w.to(torch.float16 if fp16 else torch.bfloat16).view(torch.int16).numpy().astype(np.uint16)
+    want = np.zeros(nbytes // 2, np.uint16)
+    for c in range(nchunks):
+        for dx in range(3):
+            base = ((c * 3 + dx) * 3 * coutp * 128) // 2
+            for blk in range(3):
+                for co in range(cout):
+                    r = blk * coutp + co
+                    for j in range(64):
+                        ci = c * 64 + j
+                        if ci >= cin:
+                            break
+                        off = r * 128 + (((j // 8) ^ (r & 7)) * 16) + (j % 8) * 2
+                        want[base + off // 2] = w16[co, ci, 2 - blk, dx]
+    assert np.array_equal(out.view(np.uint16), want)
+
+
+def test_choose_th_bounds(native_lib):
+    for coutp in (16, 32, 48, 64):
+        for (n, h, w) in [(1, 720, 1280), (4, 720, 1280), (1, 64, 64), (64, 480, 640), (1, 2880, 5120)]:
+            th = native_lib.b200sr_debug_choose_th(coutp, n, h, w, 148)
+            assert 1 <= th <= 512 // coutp

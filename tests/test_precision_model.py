@@ -1,0 +1,40 @@
+"""CPU emulation of the GPU path's rounding points (tests/emulate.py) against the fp32 oracle.
+
+This is the design check behind the 16-bit format choice: bf16 RRDB trunk with an fp32 residual
+stream + fp16 HR tail passes the BASELINE gate (>= 99.9 % of pixels within 1 LSB, PSNR >= 45 dB); an all-bf16 tail
+does not on high-frequency input; SRVGG (no fp32 trunk) needs fp16 throughout.
+"""
+import torch
+
+import framewright_b200  # noqa: F401
+from emulate import emulate_rrdb, emulate_srvgg
+from framewright_b200.archs import make_synthetic_state_dict
+from oracle import oracle
+
+
+def _ref(name, sd, img):
+    return oracle.make_upsampler(name, sd).enhance(img)[0]
+
+
+def test_rrdb_mixed_formats_pass_gate():
+    name = "RealESRGAN_x4plus"
+    sd = make_synthetic_state_dict(name, 0)
+    img = oracle.synthetic_frame(40, 72, seed=3, kind="noise")
+    ref = _ref(name, sd, img)
+    got = emulate_rrdb(sd, img, tail_dtype=torch.float16, tail_w_dtype=torch.float16)
+    rep = oracle.parity_report(ref, got)
+    assert rep["frac_within_1lsb"] >= oracle.GATE_FRAC_WITHIN_1LSB and rep["psnr_db"] >= oracle.GATE_PSNR_DB, rep
+    # the all-bf16 variant is measurably worse (this is why the tail is fp16)
+    rep_bf16 = oracle.parity_report(ref, emulate_rrdb(sd, img))
+    assert rep_bf16["psnr_db"] < rep["psnr_db"] - 2.0, (rep_bf16, rep)
+
+
+def test_srvgg_fp16_passes_gate_and_beats_bf16():
+    name = "realesr-animevideov3"
+    sd = make_synthetic_state_dict(name, 0)
+    img = oracle.synthetic_frame(40, 56, seed=3, kind="mixed")
+    ref = _ref(name, sd, img)
+    fp16 = oracle.parity_report(ref, emulate_srvgg(sd, img, num_conv=16, act_dtype=torch.float16, w_dtype=torch.float16))
+    bf16 = oracle.parity_report(ref, emulate_srvgg(sd, img, num_conv=16))
+    assert fp16["frac_within_1lsb"] >= oracle.GATE_FRAC_WITHIN_1LSB and fp16["psnr_db"] >= oracle.GATE_PSNR_DB, fp16
+    assert bf16["psnr_db"] < fp16["psnr_db"] - 3.0, (bf16, fp16)  # bf16 storage is measurably worse

@@ -1,0 +1,93 @@
+"""The UNMODIFIED reference files drive the B200 host layer through the `realesrgan` / `basicsr` shims.
+
+Runs only where /root/reference is mounted (this container).  The reference package cannot be imported as a
+whole (its infrastructure/models/ directory is missing, SURVEY.md finding 4), so the hot-path modules are
+loaded with stub parent packages.  There is no GPU here: the engine behind the shim is
+replaced, for this test only, by the CPU oracle, which checks the seam (constructor arguments, `enhance`
+signature and return type, file in / file out) and not the CUDA path.
+"""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+REF = "/root/reference/src/framewright"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+
+
+@pytest.fixture()
+def ref_modules(monkeypatch):
+    import framewright_b200  # noqa: F401
+    from framewright_b200 import shims
+
+    saved = {k: v for k, v in sys.modules.items() if k == "framewright" or k.startswith("framewright.")}
+    for name, path in [("framewright", REF), ("framewright.processors", REF + "/processors"),
+                       ("framewright.processors.enhancement", REF + "/processors/enhancement"),
+                       ("framewright.utils", REF + "/utils")]:
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        monkeypatch.setitem(sys.modules, name, m)
+    monkeypatch.setattr(sys, "dont_write_bytecode", True)
+    shims.install()
+    pr = importlib.import_module("framewright.processors.pytorch_realesrgan")
+    yield pr
+    for k in [k for k in sys.modules if k == "framewright" or k.startswith("framewright.")]:
+        del sys.modules[k]
+    sys.modules.update(saved)
+
+
+def test_reference_processor_calls_shim(ref_modules, tmp_path, monkeypatch):
+    import cv2
+
+    from framewright_b200 import upsampler as up_mod
+    from framewright_b200.archs import make_synthetic_state_dict
+    from oracle import oracle
+
+    pr = ref_modules
+    created = {}
+
+    class OracleEngine:  # stands in for B200Engine (no GPU in this container)
+        def __init__(self, arch, state_dict, gpu_id=0):
+            created["arch"] = arch
+            name = next(k for k, v in up_mod.MODEL_ARCHS.items() if v == arch)
+            self.name, self.sd = name, state_dict
+
+        def upscale_host(self, frames, tile=0, tile_pad=10, pre_pad=0):
+            created["tile"] = (tile, tile_pad, pre_pad)
+            return oracle.make_upsampler(self.name, self.sd, tile=tile, tile_pad=tile_pad, pre_pad=pre_pad).enhance(frames)[0]
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(up_mod, "B200Engine", OracleEngine)
+    # the reference probes `import torch; from realesrgan import RealESRGANer; from basicsr... import RRDBNet`
+    assert pr.is_pytorch_esrgan_available() is True
+    img = oracle.synthetic_frame(24, 28, seed=2, kind="mixed")
+    cv2.imwrite(str(tmp_path / "frame_00000001.png"), img)
+    cfg = pr.PyTorchESRGANConfig(model_name="RealESRGAN_x4plus_anime_6B", scale_factor=4, tile_size=16, tile_pad=4)
+    ok, err = pr.enhance_frame_pytorch(tmp_path / "frame_00000001.png", tmp_path / "out.png", cfg)
+    assert (ok, err) == (True, None), err
+    got = cv2.imread(str(tmp_path / "out.png"), cv2.IMREAD_UNCHANGED)
+    assert created["arch"].num_block == 6 and created["tile"] == (16, 4, 0)
+    sd = make_synthetic_state_dict("RealESRGAN_x4plus_anime_6B", 0)
+    want = oracle.make_upsampler("RealESRGAN_x4plus_anime_6B", sd, tile=16, tile_pad=4, pre_pad=0).enhance(img)[0]
+    assert got.shape == (96, 112, 3) and np.array_equal(got, want)
+    pr.clear_upsampler_cache()
+
+
+def test_reference_and_mirror_expose_same_surface(ref_modules):
+    from framewright_b200 import pytorch_realesrgan as mine
+
+    pr = ref_modules
+    for name in ("PyTorchESRGANConfig", "is_pytorch_esrgan_available", "get_upsampler", "enhance_frame_pytorch",
+                 "clear_upsampler_cache", "convert_ncnn_model_name", "NCNN_TO_PYTORCH_MODEL"):
+        assert hasattr(pr, name) and hasattr(mine, name)
+    assert pr.NCNN_TO_PYTORCH_MODEL == mine.NCNN_TO_PYTORCH_MODEL
+    import dataclasses
+
+    ref_fields = [(f.name, f.default) for f in dataclasses.fields(pr.PyTorchESRGANConfig)]
+    my_fields = [(f.name, f.default) for f in dataclasses.fields(mine.PyTorchESRGANConfig)]
+    assert ref_fields == my_fields

@@ -387,6 +387,58 @@ int run_upsample(b200sr_engine* e, const void* in, void* out, int N, int H, int 
   return B200SR_OK;
 }
 
+// Regions of one `enhance` call: the whole padded frame, or upstream RealESRGANer.tile_process's tiles
+// over the padded image.  Geometry only (src/dst/n are filled in by the caller).
+std::vector<Region> plan_regions(int arch, int scale, int h, int w, int tile, int tile_pad, int pre_pad) {
+  std::vector<Region> out;
+  const int mod = (arch == B200SR_ARCH_RRDB && scale == 2) ? 2 : 1;
+  const int H1 = h + pre_pad, W1 = w + pre_pad;
+  const int Hp = (H1 + mod - 1) / mod * mod, Wp = (W1 + mod - 1) / mod * mod;
+  Region R{};
+  R.Hs = h;
+  R.Ws = w;
+  R.pre_pad = pre_pad;
+  R.H1 = H1;
+  R.W1 = W1;
+  R.dst_h = h * scale;
+  R.dst_w = w * scale;
+  if (tile <= 0) {
+    R.oy = 0;
+    R.ox = 0;
+    R.rh = Hp;
+    R.rw = Wp;
+    R.crop_y0 = 0;
+    R.crop_x0 = 0;
+    R.crop_h = h * scale;
+    R.crop_w = w * scale;
+    R.dst_y0 = 0;
+    R.dst_x0 = 0;
+    out.push_back(R);
+    return out;
+  }
+  const int tiles_x = (Wp + tile - 1) / tile, tiles_y = (Hp + tile - 1) / tile;
+  for (int ty = 0; ty < tiles_y; ++ty)
+    for (int tx = 0; tx < tiles_x; ++tx) {
+      const int in_x0 = tx * tile, in_y0 = ty * tile;
+      const int in_x1 = std::min(in_x0 + tile, Wp), in_y1 = std::min(in_y0 + tile, Hp);
+      const int pad_x0 = std::max(in_x0 - tile_pad, 0), pad_x1 = std::min(in_x1 + tile_pad, Wp);
+      const int pad_y0 = std::max(in_y0 - tile_pad, 0), pad_y1 = std::min(in_y1 + tile_pad, Hp);
+      R.oy = pad_y0;
+      R.ox = pad_x0;
+      R.rh = pad_y1 - pad_y0;
+      R.rw = pad_x1 - pad_x0;
+      R.crop_y0 = (in_y0 - pad_y0) * scale;
+      R.crop_x0 = (in_x0 - pad_x0) * scale;
+      R.dst_y0 = in_y0 * scale;
+      R.dst_x0 = in_x0 * scale;
+      R.crop_h = std::min((in_y1 - in_y0) * scale, R.dst_h - R.dst_y0);  // post_process crops the pads
+      R.crop_w = std::min((in_x1 - in_x0) * scale, R.dst_w - R.dst_x0);
+      if (R.crop_h <= 0 || R.crop_w <= 0) continue;
+      out.push_back(R);
+    }
+  return out;
+}
+
 // One forward pass over one region (whole padded frame, or one padded tile).
 int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
   const auto& d = e->desc;
@@ -695,54 +747,14 @@ int b200sr_enqueue_u8(b200sr_engine* e, const uint8_t* src_dev, uint8_t* dst_dev
   padded_dims(e, h, w, pre_pad, &Hp, &Wp);
   if ((Hp > h + pre_pad && h + pre_pad < 2) || (Wp > w + pre_pad && w + pre_pad < 2))
     return fail(e, B200SR_ERR_INVALID, "frame too small for reflect mod-padding");
-  Region R{};
-  R.src = src_dev;
-  R.dst = dst_dev;
-  R.n = n;
-  R.Hs = h;
-  R.Ws = w;
-  R.pre_pad = pre_pad;
-  R.H1 = h + pre_pad;
-  R.W1 = w + pre_pad;
-  R.dst_h = h * scale;
-  R.dst_w = w * scale;
-  if (tile == 0) {
-    R.oy = 0;
-    R.ox = 0;
-    R.rh = Hp;
-    R.rw = Wp;
-    R.crop_y0 = 0;
-    R.crop_x0 = 0;
-    R.crop_h = h * scale;
-    R.crop_w = w * scale;
-    R.dst_y0 = 0;
-    R.dst_x0 = 0;
-    return run_region(e, R, st);
+  std::vector<Region> regions = plan_regions(e->desc.arch, scale, h, w, tile, tile_pad, pre_pad);
+  for (Region R : regions) {
+    R.src = src_dev;
+    R.dst = dst_dev;
+    R.n = n;
+    int rc = run_region(e, R, st);
+    if (rc) return rc;
   }
-  // upstream RealESRGANer.tile_process over the padded image
-  const int tiles_x = (Wp + tile - 1) / tile, tiles_y = (Hp + tile - 1) / tile;
-  for (int ty = 0; ty < tiles_y; ++ty)
-    for (int tx = 0; tx < tiles_x; ++tx) {
-      const int in_x0 = tx * tile, in_y0 = ty * tile;
-      const int in_x1 = std::min(in_x0 + tile, Wp), in_y1 = std::min(in_y0 + tile, Hp);
-      const int pad_x0 = std::max(in_x0 - tile_pad, 0), pad_x1 = std::min(in_x1 + tile_pad, Wp);
-      const int pad_y0 = std::max(in_y0 - tile_pad, 0), pad_y1 = std::min(in_y1 + tile_pad, Hp);
-      R.oy = pad_y0;
-      R.ox = pad_x0;
-      R.rh = pad_y1 - pad_y0;
-      R.rw = pad_x1 - pad_x0;
-      R.crop_y0 = (in_y0 - pad_y0) * scale;
-      R.crop_x0 = (in_x0 - pad_x0) * scale;
-      R.dst_y0 = in_y0 * scale;
-      R.dst_x0 = in_x0 * scale;
-      R.crop_h = std::min((in_y1 - in_y0) * scale, R.dst_h - R.dst_y0);  // post_process crop of the pads
-      R.crop_w = std::min((in_x1 - in_x0) * scale, R.dst_w - R.dst_x0);
-      if (R.crop_h <= 0 || R.crop_w <= 0) continue;
-      const int launches_before = e->launches;
-      int rc = run_region(e, R, st);
-      if (rc) return rc;
-      (void)launches_before;
-    }
   return B200SR_OK;
 }
 
@@ -813,6 +825,47 @@ int b200sr_get_profile(b200sr_engine* e, int nclass, double* ms, double* flops, 
   }
   e->prof.clear();
   return B200SR_OK;
+}
+
+// ---- test hooks that need no GPU ----------------------------------------------------------------
+int b200sr_debug_plan_regions(int arch, int scale, int h, int w, int tile, int tile_pad, int pre_pad, int* out,
+                              int max_regions) {
+  if (!out || h <= 0 || w <= 0 || tile < 0 || tile_pad < 0 || pre_pad < 0) return -1;
+  std::vector<Region> rs = plan_regions(arch, scale, h, w, tile, tile_pad, pre_pad);
+  int n = 0;
+  for (const Region& R : rs) {
+    if (n >= max_regions) break;
+    int* o = out + n * 10;
+    o[0] = R.oy; o[1] = R.ox; o[2] = R.rh; o[3] = R.rw; o[4] = R.crop_y0; o[5] = R.crop_x0;
+    o[6] = R.crop_h; o[7] = R.crop_w; o[8] = R.dst_y0; o[9] = R.dst_x0;
+    ++n;
+  }
+  return static_cast<int>(rs.size());
+}
+
+// Packs one conv layer's weights exactly as b200sr_finalize does; returns the image size in bytes
+// (call with out == nullptr to query it).
+long long b200sr_debug_pack_weights(const float* weight, int cout, int cin, int fp16, uint8_t* out, long long out_bytes) {
+  if (!weight || cout <= 0 || cin <= 0) return -1;
+  Layer l;
+  l.cin = cin;
+  l.cout = cout;
+  l.coutp = coutp_for(cout);
+  l.fp16 = fp16 != 0;
+  l.w.assign(weight, weight + static_cast<size_t>(cout) * cin * 9);
+  std::vector<uint8_t> img = pack_weights(l);
+  if (out) {
+    if (out_bytes < static_cast<long long>(img.size())) return -1;
+    memcpy(out, img.data(), img.size());
+  }
+  return static_cast<long long>(img.size());
+}
+
+// Rows per tile the launcher would pick (wave balancing) for an output of n x h x w on `num_sms` SMs.
+int b200sr_debug_choose_th(int coutp, int n, int h, int w, int num_sms) {
+  b200sr_engine e;
+  e.num_sms = num_sms;
+  return choose_th(&e, coutp, n, h, w);
 }
 
 // ---- test hook: one tensor-core conv layer on caller-provided device tensors -------------------

@@ -79,7 +79,7 @@ struct ConvCfg {
   static constexpr int A_STAGE_BYTES = 17 * 1024;
   static constexpr int NSTAGES = (COUT >= 48) ? 4 : 6;
   static constexpr int SMEM_BYTES = 2 * WCHUNK_BYTES + NSTAGES * A_STAGE_BYTES + 1024 /*align slack*/;
-  static constexpr int NTHREADS = 192;
+  static constexpr int NTHREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 };
 
 __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
@@ -93,6 +93,13 @@ __device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&v)[8]) {
                : "l"(p)
                : "memory");
 }
+// Non-volatile variant: the compiler may hoist and batch these (used for read-only / read-before-write data).
+__device__ __forceinline__ void ld_global_256_nv(const void* p, uint32_t (&v)[8]) {
+  asm("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+      : "l"(p));
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -182,40 +189,44 @@ __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* s
     float* xa = a.xa + pix * COUT;
     float* xb = a.xb + pix * COUT;
 #pragma unroll
-    for (int g = 0; g < COUT / 8; ++g) {
-      uint32_t r[8];
-      ld_global_256(xa + g * 8, r);
-      uint32_t o[8];
+    for (int hh = 0; hh < COUT / 32; ++hh) {   // 32 channels per batch: all loads of the batch in flight together
+      uint32_t r[4][8], r0[4][8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) ld_global_256_nv(xa + hh * 32 + g * 8, r[g]);
       if constexpr (EPI == EPI_RDB5_RRDB) {
-        uint32_t r0[8];
-        ld_global_256(xb + g * 8, r0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float v = (acc[g * 8 + i] + s_bias[g * 8 + i]) * 0.2f + __uint_as_float(r[i]);
-          v = v * 0.2f + __uint_as_float(r0[i]);
-          acc[g * 8 + i] = v;
-          o[i] = __float_as_uint(v);
-        }
-        st_global_256(xb + g * 8, o);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float v = (acc[g * 8 + i] + s_bias[g * 8 + i]) * 0.2f + __uint_as_float(r[i]);
-          acc[g * 8 + i] = v;
-          o[i] = __float_as_uint(v);
-        }
+        for (int g = 0; g < 4; ++g) ld_global_256_nv(xb + hh * 32 + g * 8, r0[g]);
       }
-      st_global_256(xa + g * 8, o);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = hh * 32 + g * 8 + i;
+          float v = (acc[c] + s_bias[c]) * 0.2f + __uint_as_float(r[g][i]);
+          if constexpr (EPI == EPI_RDB5_RRDB) v = v * 0.2f + __uint_as_float(r0[g][i]);
+          acc[c] = v;
+          o[i] = __float_as_uint(v);
+        }
+        if constexpr (EPI == EPI_RDB5_RRDB) st_global_256(xb + hh * 32 + g * 8, o);
+        st_global_256(xa + hh * 32 + g * 8, o);
+      }
     }
     store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc, a.out_fp16);
   } else if constexpr (EPI == EPI_ADD_F32) {
     const float* f = a.fadd + pix * COUT;
 #pragma unroll
-    for (int g = 0; g < COUT / 8; ++g) {
-      uint32_t r[8];
-      ld_global_256(f + g * 8, r);
+    for (int hh = 0; hh < COUT / 32; ++hh) {
+      uint32_t r[4][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[g * 8 + i] = acc[g * 8 + i] + s_bias[g * 8 + i] + __uint_as_float(r[i]);
+      for (int g = 0; g < 4; ++g) ld_global_256_nv(f + hh * 32 + g * 8, r[g]);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = hh * 32 + g * 8 + i;
+          acc[c] = acc[c] + s_bias[c] + __uint_as_float(r[g][i]);
+        }
     }
     store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc, a.out_fp16);
   } else if constexpr (EPI == EPI_LAST_U8) {
@@ -250,7 +261,7 @@ __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* s
 }
 
 template <int COUT, int EPI>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(ConvCfg<COUT>::NTHREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args) {
   using Cfg = ConvCfg<COUT>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -300,102 +311,109 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
 
   const int tiles_per_img = args.xtiles * args.ytiles;
 
+  // Roles 0 and 1 run with the WHOLE warp converged (values stay in uniform registers, no
+  // per-instruction lane-election loops); a single elected lane issues the TMA / MMA instructions.
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0, phase = 0, wb = 0, wphase = 0;
-      for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
-        const int n = t / tiles_per_img;
-        const int r = t - n * tiles_per_img;
-        const int ty = r / args.xtiles;
-        const int tx = r - ty * args.xtiles;
-        const int x0 = tx * 128 - 1;
-        const int y0 = ty * TH;
-        for (int c = 0; c < args.nchunks; ++c) {
-          mbar_wait(&bar_wempty[wb], wphase ^ 1);
+    int stage = 0, phase = 0, wb = 0, wphase = 0;
+    for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
+      const int n = t / tiles_per_img;
+      const int r = t - n * tiles_per_img;
+      const int ty = r / args.xtiles;
+      const int tx = r - ty * args.xtiles;
+      const int x0 = tx * 128 - 1;
+      const int y0 = ty * TH;
+      for (int c = 0; c < args.nchunks; ++c) {
+        mbar_wait(&bar_wempty[wb], wphase ^ 1);
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&bar_wfull[wb], Cfg::WCHUNK_BYTES);
           const uint8_t* wsrc = args.wpack + static_cast<size_t>(c) * Cfg::WCHUNK_BYTES;
 #pragma unroll
           for (int d = 0; d < 3; ++d)
             bulk_load_1d(&bar_wfull[wb], sW + wb * Cfg::WCHUNK_BYTES + d * Cfg::WTILE_BYTES,
                          wsrc + d * Cfg::WTILE_BYTES, Cfg::WTILE_BYTES);
-          for (int y = -1; y <= TH; ++y) {
-            mbar_wait(&bar_empty[stage], phase ^ 1);
+        }
+        __syncwarp();
+        for (int y = -1; y <= TH; ++y) {
+          mbar_wait(&bar_empty[stage], phase ^ 1);
+          if (elect_one_sync()) {
             mbar_arrive_expect_tx(&bar_full[stage], Cfg::A_BOX_BYTES);
             tma_load_4d(&amap, &bar_full[stage], sA + stage * Cfg::A_STAGE_BYTES, c * 64, x0, y0 + y, n);
-            if (++stage == Cfg::NSTAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
           }
-          wb ^= 1;
-          if (wb == 0) wphase ^= 1;
+          __syncwarp();
+          if (++stage == Cfg::NSTAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
+        wb ^= 1;
+        if (wb == 0) wphase ^= 1;
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const bool f16 = args.in_fp16 != 0;
-      const uint32_t idesc1 = make_idesc_16(128, COUT, f16);
-      const uint32_t idesc2 = make_idesc_16(128, 2 * COUT, f16);
-      const uint32_t idesc3 = make_idesc_16(128, 3 * COUT, f16);
-      const uint64_t adesc0 = make_smem_desc(smem_u32(sA), 1024, SWZ_128B, 0);
-      const uint64_t bdesc0 = make_smem_desc(smem_u32(sW), 1024, SWZ_128B, 0);
-      int stage = 0, phase = 0, wb = 0, wphase = 0;
-      uint32_t tile_iter = 0;
-      for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x, ++tile_iter) {
-        const uint32_t rparity = (tile_iter & 1) ^ 1;  // accumulator row drained by the previous tile's epilogue
-        for (int c = 0; c < args.nchunks; ++c) {
-          const int ks = (c == args.nchunks - 1) ? args.last_ksteps : 4;
-          const bool first_chunk = (c == 0);
-          const bool last_chunk = (c == args.nchunks - 1);
-          mbar_wait(&bar_wfull[wb], wphase);
-          const uint64_t bdesc_w = bdesc0 + static_cast<uint64_t>((wb * Cfg::WCHUNK_BYTES) >> 4);
-          for (int y = -1; y <= TH; ++y) {
-            const int blk_lo = (y < 1) ? (1 - y) : 0;        // output row y-1+blk must be >= 0
-            const int blk_hi = (TH - y < 2) ? (TH - y) : 2;  // and < TH
-            const int nblk = blk_hi - blk_lo + 1;
-            if (first_chunk && blk_hi == 2) mbar_wait(&bar_rempty[y + 1], rparity);
-            mbar_wait(&bar_full[stage], phase);
-            tc_fence_after();
-            const uint32_t dcol = tmem_base + static_cast<uint32_t>((y - 1 + blk_lo) * COUT);
-            const uint64_t ad0 = adesc0 + static_cast<uint64_t>((stage * Cfg::A_STAGE_BYTES) >> 4);
-            const uint64_t bd0 = bdesc_w + static_cast<uint64_t>((blk_lo * COUT * 128) >> 4);
-            const uint32_t idesc_n = nblk == 3 ? idesc3 : (nblk == 2 ? idesc2 : idesc1);
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (k < ks) {
-                  const uint64_t ad = ad0 + static_cast<uint64_t>((dx * 128 + k * 32) >> 4);
-                  const uint64_t bd = bd0 + static_cast<uint64_t>((dx * Cfg::WTILE_BYTES + k * 32) >> 4);
-                  if (dx == 0 && k == 0 && first_chunk && blk_hi == 2) {
-                    // accumulator row y+1 is touched for the first time: overwrite it, accumulate the others
-                    if (nblk > 1) umma_bf16(dcol, ad, bd, nblk == 3 ? idesc2 : idesc1, 1);
-                    umma_bf16(dcol + (nblk - 1) * COUT, ad, bd + static_cast<uint64_t>(((nblk - 1) * COUT * 128) >> 4),
-                              idesc1, 0);
-                  } else {
-                    umma_bf16(dcol, ad, bd, idesc_n, 1);
-                  }
-                }
-              }
+    const bool f16 = args.in_fp16 != 0;
+    const uint32_t idesc1 = make_idesc_16(128, COUT, f16);
+    const uint32_t idesc2 = make_idesc_16(128, 2 * COUT, f16);
+    const uint32_t idesc3 = make_idesc_16(128, 3 * COUT, f16);
+    const uint64_t adesc0 = make_smem_desc(smem_u32(sA), 1024, SWZ_128B, 0);
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(sW), 1024, SWZ_128B, 0);
+    int stage = 0, phase = 0, wb = 0, wphase = 0;
+    uint32_t tile_iter = 0;
+    for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x, ++tile_iter) {
+      const uint32_t rparity = (tile_iter & 1) ^ 1;  // accumulator row drained by the previous tile's epilogue
+      for (int c = 0; c < args.nchunks; ++c) {
+        const int ks = (c == args.nchunks - 1) ? args.last_ksteps : 4;
+        const bool first_chunk = (c == 0);
+        const bool last_chunk = (c == args.nchunks - 1);
+        mbar_wait(&bar_wfull[wb], wphase);
+        const uint64_t bdesc_w = bdesc0 + static_cast<uint64_t>((wb * Cfg::WCHUNK_BYTES) >> 4);
+        for (int y = -1; y <= TH; ++y) {
+          const int blk_lo = (y < 1) ? (1 - y) : 0;        // output row y-1+blk must be >= 0
+          const int blk_hi = (TH - y < 2) ? (TH - y) : 2;  // and < TH
+          const int nblk = blk_hi - blk_lo + 1;
+          const bool new_row = first_chunk && blk_hi == 2;  // accumulator row y+1 is touched for the first time
+          if (new_row) mbar_wait(&bar_rempty[y + 1], rparity);
+          mbar_wait(&bar_full[stage], phase);
+          tc_fence_after();
+          const uint32_t dcol = tmem_base + static_cast<uint32_t>((y - 1 + blk_lo) * COUT);
+          const uint64_t ad0 = adesc0 + static_cast<uint64_t>((stage * Cfg::A_STAGE_BYTES) >> 4);
+          const uint64_t bd0 = bdesc_w + static_cast<uint64_t>((blk_lo * COUT * 128) >> 4);
+          const uint32_t idesc_n = nblk == 3 ? idesc3 : (nblk == 2 ? idesc2 : idesc1);
+          if (elect_one_sync()) {
+            if (new_row) {
+              // overwrite the new row's block, accumulate into the older rows' blocks
+              if (nblk > 1) umma_bf16(dcol, ad0, bd0, nblk == 3 ? idesc2 : idesc1, 1);
+              umma_bf16(dcol + (nblk - 1) * COUT, ad0, bd0 + static_cast<uint64_t>(((nblk - 1) * COUT * 128) >> 4),
+                        idesc1, 0);
+            } else {
+              umma_bf16(dcol, ad0, bd0, idesc_n, 1);
             }
-            umma_commit(&bar_empty[stage]);                               // stage reusable once these MMAs retire
-            if (last_chunk && y >= 1) umma_commit(&bar_rfull[y - 1]);     // output row y-1 is complete
-            if (++stage == Cfg::NSTAGES) {
-              stage = 0;
-              phase ^= 1;
+#pragma unroll
+            for (int i = 1; i < 12; ++i) {
+              const int dx = i >> 2, k = i & 3;
+              if (k < ks)
+                umma_bf16(dcol, ad0 + static_cast<uint64_t>((dx * 128 + k * 32) >> 4),
+                          bd0 + static_cast<uint64_t>((dx * Cfg::WTILE_BYTES + k * 32) >> 4), idesc_n, 1);
             }
+            umma_commit(&bar_empty[stage]);                             // stage reusable once these MMAs retire
+            if (last_chunk && y >= 1) umma_commit(&bar_rfull[y - 1]);   // output row y-1 is complete
+            if (y == TH) umma_commit(&bar_wempty[wb]);                  // weight buffer reusable
           }
-          umma_commit(&bar_wempty[wb]);
-          wb ^= 1;
-          if (wb == 0) wphase ^= 1;
+          __syncwarp();
+          if (++stage == Cfg::NSTAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
+        wb ^= 1;
+        if (wb == 0) wphase ^= 1;
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps (2..5)
+    // ------------------------------------------------------------ epilogue warps (2..9)
+    // Two groups of four warps; group g drains tile rows Y = g, g+2, ... (doubles the loads in flight).
+    const int eg = (warp - 2) >> 2;
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;             // pixel within the 128-wide tile == TMEM lane
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -407,7 +425,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
       const int tx = r - ty * args.xtiles;
       const int x = tx * 128 + m;
       const int y0 = ty * TH;
-      for (int Y = 0; Y < TH; ++Y) {
+      if constexpr (EPI == EPI_RDB5 || EPI == EPI_RDB5_RRDB || EPI == EPI_ADD_F32) {
+        // pull this tile's fp32 residual rows towards L2 while the MMAs run
+        if (x < args.W) {
+          for (int Y = eg; Y < TH; Y += 2) {
+            const int y = y0 + Y;
+            if (y >= args.H) break;
+            const size_t pix = (static_cast<size_t>(n) * args.H + y) * args.W + x;
+            if constexpr (EPI == EPI_ADD_F32) {
+              prefetch_l2(args.fadd + pix * COUT);
+              prefetch_l2(args.fadd + pix * COUT + 32);
+            } else {
+              prefetch_l2(args.xa + pix * COUT);
+              prefetch_l2(args.xa + pix * COUT + 32);
+              if constexpr (EPI == EPI_RDB5_RRDB) {
+                prefetch_l2(args.xb + pix * COUT);
+                prefetch_l2(args.xb + pix * COUT + 32);
+              }
+            }
+          }
+        }
+      }
+      for (int Y = eg; Y < TH; Y += 2) {
         mbar_wait(&bar_rfull[Y], tile_iter & 1);
         tc_fence_after();
         float acc[COUT];

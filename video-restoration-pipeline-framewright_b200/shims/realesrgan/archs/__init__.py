@@ -1,0 +1,1 @@
+__b200sr_shim__ = True
