@@ -220,7 +220,7 @@ int launch_conv_inst(b200sr_engine* e, const CUtensorMap& amap, const ConvArgs& 
     CUDA_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done[e->device & 15] = true;
   }
-  int grid = std::min(a.ntiles, e->opt_max_ctas > 0 ? e->opt_max_ctas : e->num_sms);
+  int grid = std::min(a.ntiles, e->opt_max_ctas > 0 ? e->opt_max_ctas : e->num_sms * Cfg::CTAS_PER_SM);
   kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>>(amap, a);
   CUDA_TRY(e, cudaGetLastError());
   e->launches++;
@@ -229,10 +229,10 @@ int launch_conv_inst(b200sr_engine* e, const CUtensorMap& amap, const ConvArgs& 
 
 // Rows per tile: fill the 512 TMEM columns unless a smaller TH balances the waves better.
 int choose_th(const b200sr_engine* e, int coutp, int N, int H, int W) {
-  const int maxth = 512 / coutp;
+  const int maxth = (512 / B200SR_CTAS_PER_SM) / coutp;
   if (e->opt_force_th > 0) return std::min(e->opt_force_th, maxth);
   const int xt = (W + 127) / 128;
-  const int slots = e->opt_max_ctas > 0 ? e->opt_max_ctas : e->num_sms;
+  const int slots = e->opt_max_ctas > 0 ? e->opt_max_ctas : e->num_sms * B200SR_CTAS_PER_SM;
   double best = 1e30;
   int best_th = maxth;
   for (int th = maxth; th >= 1; --th) {

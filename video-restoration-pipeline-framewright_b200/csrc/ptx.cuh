@@ -44,10 +44,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, P1;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware, do not spin
       : "memory");
   return ok != 0;
 }
@@ -145,6 +145,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+
+// Zero `NCOL` consecutive TMEM columns of this warp's 32 lanes (NCOL = 16 or 32).
+template <int NCOL>
+__device__ __forceinline__ void tmem_zero(uint32_t taddr) {
+  const uint32_t z = 0;
+  if constexpr (NCOL == 32) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr),
+        "r"(z)
+        : "memory");
+  } else {
+    static_assert(NCOL == 16, "tmem_zero supports 16 or 32 columns");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(
+                     taddr),
+                 "r"(z)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // --------------------------------------------------------------- descriptors
 enum : uint32_t { SWZ_NONE = 0, SWZ_128B = 2, SWZ_64B = 4, SWZ_32B = 6 };

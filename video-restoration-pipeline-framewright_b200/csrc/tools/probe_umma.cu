@@ -92,7 +92,7 @@ t1_kernel(const __grid_constant__ CUtensorMap amap, const uint8_t* __restrict__ 
 }
 
 // ----------------------------------------------------------------------------- T2
-template <int N>
+template <int N, int NACC>
 __global__ void __launch_bounds__(128, 1) t2_kernel(int niter, long long* cyc_out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(128, 1) t2_kernel(int niter, long long* cyc_ou
       for (int j = 0; j < 24; ++j) {
         const uint32_t aoff = ((j & 3) * 17408 + (j % 3) * 128 + ((j >> 2) & 3) * 32) >> 4;
         const uint32_t boff = (((j >> 2) & 3) * 32) >> 4;
-        umma_bf16(tmem + ((j & 1) ? 256 : 0), abase + aoff, bbase + boff, idesc, 1);
+        umma_bf16(tmem + (N <= 128 ? (j % NACC) * 128 : (j % (NACC > 2 ? 2 : NACC)) * 256), abase + aoff, bbase + boff, idesc, 1);
       }
     }
     umma_commit(&bar_done);
@@ -137,12 +137,12 @@ __global__ void __launch_bounds__(128, 1) t2_kernel(int niter, long long* cyc_ou
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-template <int N>
+template <int N, int NACC>
 static void run_t2(int grid, long long* dc) {
   const int niter = 24 * 256;
-  CK(cudaFuncSetAttribute(t2_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(t2_kernel<N, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   for (int rep = 0; rep < 2; ++rep) {
-    t2_kernel<N><<<grid, 128, 200 * 1024>>>(niter, dc);
+    t2_kernel<N, NACC><<<grid, 128, 200 * 1024>>>(niter, dc);
     CK(cudaDeviceSynchronize());
   }
   std::vector<long long> hc(grid);
@@ -152,7 +152,7 @@ static void run_t2(int grid, long long* dc) {
     mx = c > mx ? c : mx;
     mn = c < mn ? c : mn;
   }
-  printf("T2 grid=%3d SW128 N=%3d : %.1f cyc/mma (min %.1f)  math-floor=%d  smem(A+B)@128B/cyc=%d\n", grid, N,
+  printf("T2 grid=%3d SW128 N=%3d accumulators=%d : %.1f cyc/mma (min %.1f)  math-floor=%d  smem(A+B)@128B/cyc=%d\n", grid, N, NACC,
          (double)mx / niter, (double)mn / niter, N / 2, (4096 + N * 32) / 128);
 }
 
@@ -231,6 +231,161 @@ t4_kernel(const __grid_constant__ CUtensorMap amap, int box_bytes, int niter, in
   }
 }
 
+
+// ----------------------------------------------------------------------------- T5
+// MMA rate (N=96, one accumulator range) with concurrent TMA fills of other smem stages and/or
+// concurrent TMEM loads by 4..8 "epilogue" warps.  mode bit0: TMA traffic, bit1: LDTM traffic, bit2: 8 polling warps.
+__global__ void __launch_bounds__(320, 1)
+t5_kernel(const __grid_constant__ CUtensorMap amap, int niter, int mode, int tma_per_12, long long* cyc_out,
+          float* sink) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_done, bar_tma[4], bar_never;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ volatile int stop_flag;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (100 * 1024) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + (i & 0xff);
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_done, 1);
+    mbar_init(&bar_never, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_tma[i], 1);
+    stop_flag = 0;
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  uint8_t* sB = smem + 4 * 17408;              // 24 KB of B
+  uint8_t* sT = smem + 4 * 17408 + 32 * 1024;  // 4 TMA landing stages (not read by the MMAs)
+  if (warp == 0) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 96);
+      const uint64_t abase = make_smem_desc(smem_u32(smem), 1024, SWZ_128B, 0);
+      const uint64_t bbase = make_smem_desc(smem_u32(sB), 1024, SWZ_128B, 0);
+      long long t0 = clock64();
+      for (int it = 0; it < niter; it += 24) {
+#pragma unroll
+        for (int j = 0; j < 24; ++j) {
+          const uint32_t aoff = ((j & 3) * 17408 + (j % 3) * 128 + ((j >> 2) & 3) * 32) >> 4;
+          const uint32_t boff = (((j >> 2) & 3) * 32 + (j % 3) * 6144) >> 4;
+          umma_bf16(tmem + 128, abase + aoff, bbase + boff, idesc, 1);
+        }
+      }
+      umma_commit(&bar_done);
+      mbar_wait(&bar_done, 0);
+      long long t1 = clock64();
+      cyc_out[blockIdx.x] = t1 - t0;
+      stop_flag = 1;
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && (mode & 1)) {
+      // TMA traffic: tma_per_12 boxes per 12 MMAs (~ per 672 cycles at full rate); unpaced if 0
+      int it = 0;
+      long long tstart = clock64();
+      while (!stop_flag) {
+        int s = it & 3;
+        if (it >= 4) mbar_wait(&bar_tma[s], ((it >> 2) - 1) & 1);
+        if (tma_per_12 > 0) {
+          long long target = tstart + (long long)it * 672 / tma_per_12;
+          while (clock64() < target && !stop_flag) {
+          }
+        }
+        mbar_arrive_expect_tx(&bar_tma[s], 130 * 128);
+        tma_load_4d(&amap, &bar_tma[s], sT + s * 17408, ((it + blockIdx.x) % 3) * 64, ((it * 7 + blockIdx.x) % 9) * 128 - 1,
+                    (it + blockIdx.x * 5) % 64, 0);
+        ++it;
+      }
+      // drain
+      for (int k = (it > 4 ? it - 4 : 0); k < it; ++k) mbar_wait(&bar_tma[k & 3], (k >> 2) & 1);
+    }
+  } else {
+    if ((mode & 2) && warp < 6) {
+      uint32_t acc = 0;
+      const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+      while (!stop_flag) {
+        uint32_t v[32];
+        tmem_ld32(tl + 256, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc += v[i];
+      }
+      sink[blockIdx.x * blockDim.x + threadIdx.x] = (float)acc;
+    } else if (mode & 4) {
+      // polling warps: spin on a barrier that never completes (what idle epilogue warps do)
+      while (!stop_flag) {
+        if (mbar_try_wait(&bar_never, 0)) break;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+
+// ----------------------------------------------------------------------------- T6
+// MMA bursts as the conv kernel issues them: 12 x (M128 x N96 x K16) then `ncommit` tcgen05.commit to distinct
+// mbarriers; accumulator column offset `col0 + 32 * (burst % nrows)`.
+__global__ void __launch_bounds__(128, 1) t6_kernel(int nburst, int ncommit, int col0, int nrows, long long* cyc_out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_done, bar_c[4];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (100 * 1024) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + (i & 0xff);
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_done, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_c[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 0) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 96);
+    const uint64_t abase = make_smem_desc(smem_u32(smem), 1024, SWZ_128B, 0);
+    const uint64_t bbase = make_smem_desc(smem_u32(smem) + 4 * 17408, 1024, SWZ_128B, 0);
+    long long t0 = clock64();
+    for (int b = 0; b < nburst; ++b) {
+      const uint32_t dcol = tmem + col0 + 32 * (b % nrows);
+      const uint64_t ad0 = abase + (uint64_t)(((b & 3) * 17408) >> 4);
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const int dx = i >> 2, k = i & 3;
+          umma_bf16(dcol, ad0 + (uint64_t)((dx * 128 + k * 32) >> 4), bbase + (uint64_t)((dx * 12288 + k * 32) >> 4), idesc, 1);
+        }
+        for (int c = 0; c < ncommit; ++c) umma_commit(&bar_c[c]);
+      }
+      __syncwarp();
+    }
+    if (elect_one_sync()) {
+      umma_commit(&bar_done);
+      mbar_wait(&bar_done, 0);
+      long long t1 = clock64();
+      cyc_out[blockIdx.x] = t1 - t0;
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 int main(int argc, char** argv) {
   int dev = 0;
   CK(cudaSetDevice(dev));
@@ -242,7 +397,7 @@ int main(int argc, char** argv) {
     return 3;
   }
   // ------------------------------ T1
-  {
+  if (getenv("PROBE_ALL")) {
     const int W = 200, H = 2, C = 64;
     std::vector<__nv_bfloat16> hx((size_t)H * W * C);
     srand(1);
@@ -323,24 +478,30 @@ int main(int argc, char** argv) {
     cudaFree(db);
   }
   // ------------------------------ T2
-  {
+  if (getenv("PROBE_ALL")) {
     long long* dc;
     CK(cudaMalloc(&dc, 148 * 8));
-    for (int grid : {1, 148}) {
-      run_t2<16>(grid, dc);
-      run_t2<32>(grid, dc);
-      run_t2<48>(grid, dc);
-      run_t2<64>(grid, dc);
-      run_t2<96>(grid, dc);
-      run_t2<128>(grid, dc);
-      run_t2<144>(grid, dc);
-      run_t2<192>(grid, dc);
-      run_t2<256>(grid, dc);
+    for (int grid : {148}) {
+      run_t2<32, 1>(grid, dc);
+      run_t2<32, 2>(grid, dc);
+      run_t2<32, 4>(grid, dc);
+      run_t2<64, 1>(grid, dc);
+      run_t2<64, 2>(grid, dc);
+      run_t2<96, 1>(grid, dc);
+      run_t2<96, 2>(grid, dc);
+      run_t2<96, 3>(grid, dc);
+      run_t2<96, 4>(grid, dc);
+      run_t2<128, 1>(grid, dc);
+      run_t2<128, 2>(grid, dc);
+      run_t2<192, 1>(grid, dc);
+      run_t2<192, 2>(grid, dc);
+      run_t2<256, 1>(grid, dc);
+      run_t2<256, 2>(grid, dc);
     }
     cudaFree(dc);
   }
   // ------------------------------ T3
-  {
+  if (getenv("PROBE_ALL")) {
     long long* dc;
     float* sink;
     CK(cudaMalloc(&dc, 148 * 8));
@@ -361,7 +522,7 @@ int main(int argc, char** argv) {
     cudaFree(sink);
   }
   // ------------------------------ T4
-  {
+  if (getenv("PROBE_ALL")) {
     const int W = 1280, H = 64, C = 192;
     __nv_bfloat16* dx;
     CK(cudaMalloc(&dx, (size_t)H * W * C * 2));
@@ -395,6 +556,61 @@ int main(int argc, char** argv) {
       }
     }
     cudaFree(dx);
+    cudaFree(dc);
+  }
+  // ------------------------------ T5
+  if (getenv("PROBE_ALL")) {
+    const int W = 1280, H = 64, C = 192;
+    __nv_bfloat16* dx;
+    CK(cudaMalloc(&dx, (size_t)H * W * C * 2));
+    CK(cudaMemset(dx, 0, (size_t)H * W * C * 2));
+    long long* dc;
+    float* sink;
+    CK(cudaMalloc(&dc, 148 * 8));
+    CK(cudaMalloc(&sink, 148 * 320 * 4));
+    CK(cudaFuncSetAttribute(t5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CUtensorMap amap;
+    if (tmap_encode_act(&amap, dx, 1, H, W, C, 64, 130, 128)) {
+      const int niter = 24 * 256;
+      struct Cfg { int mode, rate; const char* name; } cfgs[] = {
+          {0, 0, "MMA only"}, {4, 0, "MMA + 8 polling warps"}, {1, 1, "MMA + TMA 1 box / 12 MMA"},
+          {1, 2, "MMA + TMA 2 boxes / 12 MMA"}, {1, 0, "MMA + TMA unpaced"}, {2, 0, "MMA + 4 warps LDTM"},
+          {3, 1, "MMA + TMA 1/12 + LDTM"}, {7, 1, "MMA + TMA 1/12 + LDTM + polling"}};
+      for (auto& c : cfgs) {
+        for (int rep = 0; rep < 2; ++rep) {
+          t5_kernel<<<148, 320, 220 * 1024>>>(amap, niter, c.mode, c.rate, dc, sink);
+          CK(cudaDeviceSynchronize());
+        }
+        std::vector<long long> hc(148);
+        CK(cudaMemcpy(hc.data(), dc, 148 * 8, cudaMemcpyDeviceToHost));
+        long long mx = 0;
+        for (auto v : hc) mx = v > mx ? v : mx;
+        printf("T5 N=96 %-34s : %.1f cyc/mma\n", c.name, (double)mx / niter);
+      }
+    }
+    cudaFree(dx);
+    cudaFree(dc);
+    cudaFree(sink);
+  }
+  // ------------------------------ T6
+  {
+    long long* dc;
+    CK(cudaMalloc(&dc, 148 * 8));
+    CK(cudaFuncSetAttribute(t6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const int nburst = 512;
+    struct Cfg { int ncommit, col0, nrows; } cfgs[] = {{0, 0, 1}, {1, 0, 1}, {2, 0, 1}, {3, 0, 1}, {1, 32, 1}, {1, 0, 8}, {1, 32, 12}, {2, 32, 12}};
+    for (auto& c : cfgs) {
+      for (int rep = 0; rep < 2; ++rep) {
+        t6_kernel<<<148, 128, 200 * 1024>>>(nburst, c.ncommit, c.col0, c.nrows, dc);
+        CK(cudaDeviceSynchronize());
+      }
+      std::vector<long long> hc(148);
+      CK(cudaMemcpy(hc.data(), dc, 148 * 8, cudaMemcpyDeviceToHost));
+      long long mx = 0;
+      for (auto v : hc) mx = v > mx ? v : mx;
+      printf("T6 bursts of 12 x N96, commits/burst=%d col0=%d rows=%d : %.1f cyc/mma\n", c.ncommit, c.col0, c.nrows,
+             (double)mx / (nburst * 12));
+    }
     cudaFree(dc);
   }
   printf("probe done\n");
