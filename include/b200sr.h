@@ -87,10 +87,14 @@ int b200sr_last_launch_count(const b200sr_engine* e);
 int b200sr_set_option(b200sr_engine* e, const char* key, int value);
 
 /* Per-kernel-class timing collected while option "profile" is 1 (CUDA events around every launch).
- * Arrays of length nclass >= 10, indexed: 0 conv<32,act> 1 conv<64,act> 2 conv<64,prelu> 3 conv<64,rdb5>
- * 4 conv<64,rdb5+rrdb> 5 conv<64,add> 6 conv<16,last_u8> 7 conv<48,srvgg_last> 8 first_conv 9 upsample2x.
+ * Arrays of length nclass >= 11, indexed: 0 conv<32,act> 1 conv<64,act> 2 conv<64,prelu> 3 conv<64,rdb5>
+ * 4 conv<64,rdb5+rrdb> 5 conv<64,add> 6 conv<16,last_u8> 7 conv<48,srvgg_last> 8 first_conv 9 upsample2x 10 rdb_fused.
  * flops = algorithmic FLOPs (true channel counts).  Clears the collected records. */
 int b200sr_get_profile(b200sr_engine* e, int nclass, double* ms, double* flops, int* launches);
+
+/* Dev tool: wait / issue cycle counters of the last fused-RDB launch, 16 long long per CTA (needs option
+ * "rdb_stats" = 1).  Returns the number of CTAs written. */
+int b200sr_debug_rdb_stats(b200sr_engine* e, long long* out, int max_ctas);
 
 /* Host-only test hooks (no GPU needed).
  * plan_regions: the regions one enhance call is split into (tile == 0: one region; else upstream
@@ -102,6 +106,9 @@ int b200sr_debug_plan_regions(int arch, int scale, int h, int w, int tile, int t
                               int max_regions);
 long long b200sr_debug_pack_weights(const float* weight, int cout, int cin, int fp16, uint8_t* out, long long out_bytes);
 int b200sr_debug_choose_th(int coutp, int n, int h, int w, int num_sms);
+/* rdb_items: work list of the fused-RDB kernel; 8 ints per item: k n y0 rows tx flag_base dep_base0 dep_base1
+ * (counter of 8-row block b of a conv = base + b).  Returns the item count. */
+int b200sr_debug_rdb_items(int n, int h, int w, int* out, int max_items);
 
 /* Test hook: one tensor-core 3x3 conv layer on caller-provided device tensors (bf16 NHWC in/out,
  * fp32 OIHW host weights).  epi 0: leaky(slope) ; epi 1: PReLU(prelu_host[64]); fp16 != 0: tensors and

@@ -90,3 +90,21 @@ def test_device_path_matches_host_path(native_lib):
     assert np.array_equal(dev[0].cpu().numpy(), host)
     assert eng.last_launch_count > 0
     eng.close()
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 70, 200), (2, 150, 300), (1, 333, 517), (3, 64, 1280)])
+def test_fused_rdb_kernel_is_bit_identical_to_per_conv_kernels(native_lib, n, h, w):
+    """The persistent fused-RDB kernel (cross-CTA dependency counters, L2-resident intermediates) computes every
+    pixel with the same operation order as the five per-conv launches: outputs must be bit-identical, and stay so
+    when repeated (any dependency race shows up as a mismatch)."""
+    from oracle import oracle
+
+    eng, _ = _engine("RealESRGAN_x4plus_anime_6B")
+    frames = np.stack([oracle.synthetic_frame(h, w, seed=40 + i, kind="noise") for i in range(n)])
+    eng.set_option("fused_rdb", 0)
+    ref = eng.upscale_host(frames)
+    eng.set_option("fused_rdb", 1)
+    for _ in range(3):
+        got = eng.upscale_host(frames)
+        assert np.array_equal(got, ref)
+    eng.close()

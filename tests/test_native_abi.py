@@ -133,3 +133,41 @@ def test_choose_th_bounds(native_lib):
         for (n, h, w) in [(1, 720, 1280), (4, 720, 1280), (1, 64, 64), (64, 480, 640), (1, 2880, 5120)]:
             th = native_lib.b200sr_debug_choose_th(coutp, n, h, w, 148)
             assert 1 <= th <= 512 // coutp
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 720, 1280), (2, 45, 300), (1, 16, 128), (1, 7, 50), (1, 333, 517)])
+def test_fused_rdb_work_list(native_lib, n, h, w):
+    """Work list of the fused-RDB kernel: every (conv, frame, row, column) is covered exactly once, item row
+    ranges start on 8-row block boundaries (completion counters are per block), and every 8-row block an item
+    reads from a lower conv (its own rows +-1) is produced entirely by EARLIER items of the list -- so in-order
+    round-robin execution on co-resident CTAs cannot deadlock."""
+    cap = 200000
+    buf = (ctypes.c_int * (8 * cap))()
+    cnt = native_lib.b200sr_debug_rdb_items(n, h, w, buf, cap)
+    assert 0 < cnt <= cap
+    items = np.frombuffer(buf, dtype=np.int32, count=cnt * 8).reshape(cnt, 8)
+    xt = (w + 127) // 128
+    nblk = (h + 7) // 8
+    cover = np.zeros((5, n, h, xt), np.int32)
+    last_writer = np.full((n, 4, nblk), -1, np.int64)     # index of the last item that stores into the block
+    for i, (k, fn, y0, rows, tx, fb, d0, d1) in enumerate(items):
+        assert 0 <= k < 5 and 1 <= rows <= (16 if k < 4 else 8) and y0 >= 0 and y0 + rows <= h
+        assert y0 % 8 == 0
+        cover[k, fn, y0:y0 + rows, tx] += 1
+        if k < 4:
+            assert fb == (fn * 4 + k) * nblk
+            for b in range(y0 // 8, (y0 + rows - 1) // 8 + 1):
+                last_writer[fn, k, b] = i
+        else:
+            assert fb == -1
+    assert cover.min() == 1 and cover.max() == 1
+    nchunks = [1, 2, 2, 3, 3]
+    for i, (k, fn, y0, rows, tx, fb, d0, d1) in enumerate(items):
+        for c, dbase in ((1, d0), (2, d1)):
+            if c >= nchunks[k]:
+                assert dbase == -1
+                continue
+            dep = min(2 * c - 1, k - 1)
+            assert dbase == (fn * 4 + dep) * nblk
+            for r in range(max(y0 - 1, 0), min(y0 + rows + 1, h)):
+                assert 0 <= last_writer[fn, dep, r // 8] < i, (i, k, r)

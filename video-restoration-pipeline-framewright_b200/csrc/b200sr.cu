@@ -16,6 +16,7 @@
 #include "../../include/b200sr.h"
 #include "conv3x3_tc.cuh"
 #include "pointwise.cuh"
+#include "rdb_fused.cuh"
 #include "tmap.h"
 
 using namespace b200sr;
@@ -79,6 +80,14 @@ struct b200sr_engine {
   int opt_max_ctas = 0;     // 0 = one per SM
   bool attrs_set = false;
   // optional per-kernel-class timing (CUDA events around every launch; option "profile")
+  int opt_fused_rdb = 1;    // run each RDB as one persistent kernel (L2-resident intermediates)
+  int opt_rdb_stats = 0;    // dev: collect per-CTA cycle counters of the k-th fused launch of a forward pass (1-based)
+  int rdb_launch_idx = 0;
+  long long* d_rdb_stats = nullptr;
+  // fused-RDB item table (depends only on N, H, W)
+  int rdb_n = 0, rdb_h = 0, rdb_w = 0, rdb_nitems = 0, rdb_nflags = 0;
+  RdbItem* d_rdb_items = nullptr;
+  int* d_rdb_flags = nullptr;
   int opt_profile = 0;
   struct ProfRec {
     int cls;
@@ -91,7 +100,7 @@ struct b200sr_engine {
 
 enum ProfClass {
   PC_CONV32_ACT = 0, PC_CONV64_ACT, PC_CONV64_PRELU, PC_CONV64_RDB5, PC_CONV64_RDB5_RRDB, PC_CONV64_ADD,
-  PC_CONV16_LAST, PC_CONV48_SRVGG_LAST, PC_FIRST, PC_UPSAMPLE, PC_COUNT
+  PC_CONV16_LAST, PC_CONV48_SRVGG_LAST, PC_FIRST, PC_UPSAMPLE, PC_RDB_FUSED, PC_COUNT
 };
 
 namespace {
@@ -296,14 +305,15 @@ struct Region {
 
 size_t region_ws_bytes(const b200sr_engine* e, int N, int H, int W) {
   const size_t px = static_cast<size_t>(N) * H * W;
+  const size_t pxt = static_cast<size_t>(N) * H * ((W + 127) / 128) * 128;   // fp32 trunk: width padded to 128
   size_t total = 0;
   auto add = [&](size_t b) { total += align_up(b, 1024); };
   if (e->desc.arch == B200SR_ARCH_RRDB) {
     add(px * 192 * 2);
     add(px * 192 * 2);            // dense ping-pong
-    add(px * 64 * 4);
-    add(px * 64 * 4);
-    add(px * 64 * 4);             // xa, xb, f0
+    add(pxt * 64 * 4);
+    add(pxt * 64 * 4);
+    add(pxt * 64 * 4);            // xa, xb, f0 (tile-interleaved layout)
     add(px * 64 * 2);             // conv_body out
     add(px * 4 * 64 * 2);
     add(px * 4 * 64 * 2);         // 2x: upsampled, conv_up1 out
@@ -334,6 +344,127 @@ int ensure_ws(b200sr_engine* e, size_t bytes, cudaStream_t st) {
   }
   e->ws = static_cast<uint8_t*>(p);
   e->ws_bytes = bytes;
+  return B200SR_OK;
+}
+
+// ---- fused RDB: item table (skewed row strips) ------------------------------------------------------
+constexpr int RDB_STRIP = 16;   // rows per strip (= rows per conv1..4 item; conv5 items have 8)
+int RDB_STEP_OFF[5] = {0, 1, 2, 3, 5};   // step in which conv k reaches strip s: s + RDB_STEP_OFF[k] (option rdb_off)
+
+// Strip s of conv k covers rows [16 s - 8 k, 16 s + 16 - 8 k): every conv is shifted up by 8 rows relative to
+// its predecessor, so the rows an item reads (its own +-1) of a lower conv belong to items earlier in the list.
+void build_rdb_items(int N, int H, int W, std::vector<RdbItem>& items, int* nflags) {
+  const int S = (H + 32 + RDB_STRIP - 1) / RDB_STRIP;
+  const int xt = (W + 127) / 128;
+  const int nblk = (H + 7) / 8;
+  *nflags = N * 4 * nblk;
+  items.clear();
+  for (int n = 0; n < N; ++n)
+    for (int t = 0; t < S + RDB_STEP_OFF[4]; ++t)
+      for (int k = 0; k < 5; ++k) {
+        // in step t conv k works on strip t - RDB_STEP_OFF[k]: its producer ran one or two steps (~60 items each)
+        // earlier.  conv5 trails conv4 by two steps: conv4 items are the longest and finish their rows last,
+        // conv5 items are short and reach their dependent chunk early.
+        const int s = t - RDB_STEP_OFF[k];
+        if (s < 0 || s >= S) continue;
+        const int lo = std::max(0, s * RDB_STRIP - 8 * k), hi = std::min(H, (s + 1) * RDB_STRIP - 8 * k);
+        if (lo >= hi) continue;
+        const int th = k < 4 ? 16 : 8;
+        for (int y0 = lo; y0 < hi; y0 += th)
+          for (int tx = 0; tx < xt; ++tx) {
+            RdbItem it{};
+            it.k = k;
+            it.n = n;
+            it.y0 = y0;
+            it.rows = std::min(th, hi - y0);
+            it.tx = tx;
+            it.flag_base = k < 4 ? (n * 4 + k) * nblk : -1;
+            for (int c = 1; c <= 2; ++c) {
+              // chunk c holds channels [64c, 64c+64): x1,x2 (c = 1) or x3,x4 (c = 2); newest producer below k
+              const int dep = std::min(2 * c - 1, k - 1);
+              const bool used = (k >= 1) && (c == 1 || k >= 3);
+              it.dep_base[c - 1] = used ? (n * 4 + dep) * nblk : -1;
+            }
+            items.push_back(it);
+          }
+      }
+}
+
+int ensure_rdb_table(b200sr_engine* e, int N, int H, int W, cudaStream_t st) {
+  if (e->d_rdb_items && e->rdb_n == N && e->rdb_h == H && e->rdb_w == W) return B200SR_OK;
+  CUDA_TRY(e, cudaStreamSynchronize(st));
+  if (e->d_rdb_items) cudaFree(e->d_rdb_items);
+  if (e->d_rdb_flags) cudaFree(e->d_rdb_flags);
+  e->d_rdb_items = nullptr;
+  e->d_rdb_flags = nullptr;
+  std::vector<RdbItem> items;
+  int nflags = 0;
+  build_rdb_items(N, H, W, items, &nflags);
+  CUDA_TRY(e, cudaMalloc(&e->d_rdb_items, items.size() * sizeof(RdbItem)));
+  CUDA_TRY(e, cudaMalloc(&e->d_rdb_flags, static_cast<size_t>(nflags + 1) * sizeof(int)));   // + item counter
+  CUDA_TRY(e, cudaMemcpy(e->d_rdb_items, items.data(), items.size() * sizeof(RdbItem), cudaMemcpyHostToDevice));
+  e->rdb_n = N;
+  e->rdb_h = H;
+  e->rdb_w = W;
+  e->rdb_nitems = static_cast<int>(items.size());
+  e->rdb_nflags = nflags;
+  return B200SR_OK;
+}
+
+// One RDB (layers li .. li+4) as one persistent kernel.
+int launch_rdb_fused(b200sr_engine* e, int li, bool rrdb_end, __nv_bfloat16* Dcur, __nv_bfloat16* Dnext, float* xa,
+                     float* xb, int N, int H, int W, cudaStream_t st) {
+  int rc = ensure_rdb_table(e, N, H, W, st);
+  if (rc) return rc;
+  CUtensorMap amap;
+  if (!tmap_encode_act(&amap, Dcur, N, H, W, 192, 64, 130, 128)) return fail(e, B200SR_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  RdbArgs a{};
+  double flops = 0;
+  for (int k = 0; k < 5; ++k) {
+    const Layer& l = e->layers[li + k];
+    ConvArgs& c = a.L[k];
+    c.N = N;
+    c.H = H;
+    c.W = W;
+    c.nchunks = (l.cin + 63) / 64;
+    c.last_ksteps = (l.cin % 64 == 32) ? 2 : 4;
+    c.wpack = l.d_wpack;
+    c.bias = l.d_bias;
+    c.slope = 0.2f;
+    if (k < 4) {
+      c.out = Dcur;
+      c.out_pitch = 192;
+      c.out_choff = 64 + 32 * k;
+    } else {
+      c.out = Dnext;
+      c.out_pitch = 192;
+      c.out_choff = 0;
+      c.xa = xa;
+      c.xb = xb;
+    }
+    flops += 2.0 * 9.0 * l.cin * l.cout * static_cast<double>(N) * H * W;
+  }
+  a.items = e->d_rdb_items;
+  a.nitems = e->rdb_nitems;
+  a.flags = e->d_rdb_flags;
+  a.counter = e->d_rdb_flags + e->rdb_nflags;
+  a.flag_target = ((W + 127) / 128) * RDB_NEPI_WARPS;
+  a.rrdb_end = rrdb_end ? 1 : 0;
+  if (++e->rdb_launch_idx == e->opt_rdb_stats) {
+    if (!e->d_rdb_stats) CUDA_TRY(e, cudaMalloc(&e->d_rdb_stats, 148 * 16 * sizeof(long long)));
+    a.stats = e->d_rdb_stats;
+  }
+  static bool attr_done[16] = {};
+  if (!attr_done[e->device & 15]) {
+    CUDA_TRY(e, cudaFuncSetAttribute(rdb_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RDB_SMEM_BYTES));
+    attr_done[e->device & 15] = true;
+  }
+  ProfScope prof_scope(e, PC_RDB_FUSED, flops, st);
+  CUDA_TRY(e, cudaMemsetAsync(e->d_rdb_flags, 0, static_cast<size_t>(e->rdb_nflags + 1) * sizeof(int), st));
+  const int grid = std::min(a.nitems, e->opt_max_ctas > 0 ? e->opt_max_ctas : e->num_sms);
+  rdb_fused_kernel<<<grid, RDB_NTHREADS, RDB_SMEM_BYTES, st>>>(amap, a);
+  CUDA_TRY(e, cudaGetLastError());
+  e->launches++;
   return B200SR_OK;
 }
 
@@ -470,9 +601,10 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
     __nv_bfloat16* D[2];
     D[0] = reinterpret_cast<__nv_bfloat16*>(take(px * 192 * 2));
     D[1] = reinterpret_cast<__nv_bfloat16*>(take(px * 192 * 2));
-    float* xa = reinterpret_cast<float*>(take(px * 64 * 4));
-    float* xb = reinterpret_cast<float*>(take(px * 64 * 4));
-    float* f0 = reinterpret_cast<float*>(take(px * 64 * 4));
+    const size_t pxt = static_cast<size_t>(N) * H * ((W + 127) / 128) * 128;
+    float* xa = reinterpret_cast<float*>(take(pxt * 64 * 4));
+    float* xb = reinterpret_cast<float*>(take(pxt * 64 * 4));
+    float* f0 = reinterpret_cast<float*>(take(pxt * 64 * 4));
     __nv_bfloat16* U0 = reinterpret_cast<__nv_bfloat16*>(take(px * 64 * 2));
     __nv_bfloat16* U1 = reinterpret_cast<__nv_bfloat16*>(take(px * 4 * 64 * 2));
     __nv_bfloat16* U2 = reinterpret_cast<__nv_bfloat16*>(take(px * 4 * 64 * 2));
@@ -484,24 +616,30 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
     int li = 1, cur_d = 0;
     for (int b = 0; b < d.num_block; ++b)
       for (int r = 0; r < 3; ++r) {
-        ConvIO io{D[cur_d], 192, N, H, W};
-        for (int k = 0; k < 4; ++k) {
+        if (e->opt_fused_rdb) {
+          rc = launch_rdb_fused(e, li, r == 2, D[cur_d], D[cur_d ^ 1], xa, xb, N, H, W, st);
+          if (rc) return rc;
+          li += 5;
+        } else {
+          ConvIO io{D[cur_d], 192, N, H, W};
+          for (int k = 0; k < 4; ++k) {
+            ConvArgs a = base;
+            a.slope = 0.2f;
+            a.out = D[cur_d];
+            a.out_pitch = 192;
+            a.out_choff = 64 + 32 * k;
+            rc = launch_conv(e, e->layers[li++], EPI_ACT_BF16, io, a, st);
+            if (rc) return rc;
+          }
           ConvArgs a = base;
-          a.slope = 0.2f;
-          a.out = D[cur_d];
+          a.out = D[cur_d ^ 1];
           a.out_pitch = 192;
-          a.out_choff = 64 + 32 * k;
-          rc = launch_conv(e, e->layers[li++], EPI_ACT_BF16, io, a, st);
+          a.out_choff = 0;
+          a.xa = xa;
+          a.xb = xb;
+          rc = launch_conv(e, e->layers[li++], r == 2 ? EPI_RDB5_RRDB : EPI_RDB5, io, a, st);
           if (rc) return rc;
         }
-        ConvArgs a = base;
-        a.out = D[cur_d ^ 1];
-        a.out_pitch = 192;
-        a.out_choff = 0;
-        a.xa = xa;
-        a.xb = xb;
-        rc = launch_conv(e, e->layers[li++], r == 2 ? EPI_RDB5_RRDB : EPI_RDB5, io, a, st);
-        if (rc) return rc;
         cur_d ^= 1;
       }
     {  // conv_body: feat + conv_body(body(feat))
@@ -634,6 +772,9 @@ void b200sr_destroy(b200sr_engine* e) {
   for (auto* p : e->prelu_dev)
     if (p) cudaFree(p);
   if (e->ws) cudaFree(e->ws);
+  if (e->d_rdb_items) cudaFree(e->d_rdb_items);
+  if (e->d_rdb_flags) cudaFree(e->d_rdb_flags);
+  if (e->d_rdb_stats) cudaFree(e->d_rdb_stats);
   if (e->stage_in) cudaFree(e->stage_in);
   if (e->stage_out) cudaFree(e->stage_out);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -742,6 +883,7 @@ int b200sr_enqueue_u8(b200sr_engine* e, const uint8_t* src_dev, uint8_t* dst_dev
   CUDA_TRY(e, cudaSetDevice(e->device));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   e->launches = 0;
+  e->rdb_launch_idx = 0;
   const int scale = e->desc.scale;
   int Hp, Wp;
   padded_dims(e, h, w, pre_pad, &Hp, &Wp);
@@ -799,6 +941,22 @@ int b200sr_set_option(b200sr_engine* e, const char* key, int value) {
     e->opt_max_ctas = value;
     return B200SR_OK;
   }
+  if (!strcmp(key, "rdb_off")) {   // decimal digits-pairs: value = o1 + 100*o2 + 10000*o3 + 1000000*o4
+    RDB_STEP_OFF[1] = value % 100;
+    RDB_STEP_OFF[2] = (value / 100) % 100;
+    RDB_STEP_OFF[3] = (value / 10000) % 100;
+    RDB_STEP_OFF[4] = (value / 1000000) % 100;
+    e->rdb_n = 0;   // rebuild the work list
+    return B200SR_OK;
+  }
+  if (!strcmp(key, "rdb_stats")) {
+    e->opt_rdb_stats = value;
+    return B200SR_OK;
+  }
+  if (!strcmp(key, "fused_rdb")) {
+    e->opt_fused_rdb = value;
+    return B200SR_OK;
+  }
   if (!strcmp(key, "profile")) {  // 1: time every launch with CUDA events; read back with b200sr_get_profile
     e->opt_profile = value;
     return B200SR_OK;
@@ -825,6 +983,14 @@ int b200sr_get_profile(b200sr_engine* e, int nclass, double* ms, double* flops, 
   }
   e->prof.clear();
   return B200SR_OK;
+}
+
+// Dev tool: per-CTA cycle counters of the LAST fused-RDB launch (option "rdb_stats" = 1); [grid][16] long long.
+int b200sr_debug_rdb_stats(b200sr_engine* e, long long* out, int max_ctas) {
+  if (!e || !out || !e->d_rdb_stats) return -1;
+  const int n = std::min(max_ctas, std::min(e->num_sms, 148));
+  if (cudaMemcpy(out, e->d_rdb_stats, static_cast<size_t>(n) * 16 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return n;
 }
 
 // ---- test hooks that need no GPU ----------------------------------------------------------------
@@ -859,6 +1025,22 @@ long long b200sr_debug_pack_weights(const float* weight, int cout, int cin, int 
     memcpy(out, img.data(), img.size());
   }
   return static_cast<long long>(img.size());
+}
+
+// The fused-RDB work list for n frames of h x w: 8 ints per item (k n y0 rows tx flag_base dep_base[0] dep_base[1]);
+// returns the item count (may exceed max_items).
+int b200sr_debug_rdb_items(int n, int h, int w, int* out, int max_items) {
+  if (n <= 0 || h <= 0 || w <= 0) return -1;
+  std::vector<RdbItem> items;
+  int nflags = 0;
+  build_rdb_items(n, h, w, items, &nflags);
+  for (size_t i = 0; i < items.size() && static_cast<int>(i) < max_items && out; ++i) {
+    const RdbItem& it = items[i];
+    int* o = out + i * 8;
+    o[0] = it.k; o[1] = it.n; o[2] = it.y0; o[3] = it.rows; o[4] = it.tx; o[5] = it.flag_base;
+    o[6] = it.dep_base[0]; o[7] = it.dep_base[1];
+  }
+  return static_cast<int>(items.size());
 }
 
 // Rows per tile the launcher would pick (wave balancing) for an output of n x h x w on `num_sms` SMs.

@@ -123,6 +123,15 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// fp32 trunk tensors (XA, XB, F0) use a tile-interleaved layout, [n][y][x / 128][channel / 8][x % 128][channel % 8],
+// so that the per-pixel threads of a warp read and write CONSECUTIVE 32-byte chunks (1 KB per warp instruction)
+// instead of 32 different cache lines.  trunk_off() is the float offset of (pixel, channel group 0); group g is
+// TRUNK_GSTRIDE * g floats further.
+constexpr int TRUNK_GSTRIDE = 1024;
+__device__ __forceinline__ size_t trunk_off(int n, int y, int x, int H, int W) {
+  const int xt = (W + 127) >> 7;
+  return ((static_cast<size_t>(n) * H + y) * xt + (x >> 7)) * (8 * TRUNK_GSTRIDE) + static_cast<size_t>(x & 127) * 8;
+}
 __device__ __forceinline__ uint8_t quant_u8(float v) {
   v = fminf(fmaxf(v, 0.f), 1.f);
   return static_cast<uint8_t>(__float2int_rn(v * 255.0f));
@@ -201,16 +210,18 @@ __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* s
     }
     store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc, a.out_fp16);
   } else if constexpr (EPI == EPI_RDB5 || EPI == EPI_RDB5_RRDB) {
-    float* xa = a.xa + pix * COUT;
-    float* xb = a.xb + pix * COUT;
+    static_assert(COUT == 64, "trunk epilogues are 64-channel");
+    const size_t toff = trunk_off(n, y, x, a.H, a.W);
+    float* xa = a.xa + toff;
+    float* xb = a.xb + toff;
 #pragma unroll
     for (int hh = 0; hh < COUT / 32; ++hh) {   // 32 channels per batch: all loads of the batch in flight together
       uint32_t r[4][8], r0[4][8];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) ld_global_256_nv(xa + hh * 32 + g * 8, r[g]);
+      for (int g = 0; g < 4; ++g) ld_global_256_nv(xa + (hh * 4 + g) * TRUNK_GSTRIDE, r[g]);
       if constexpr (EPI == EPI_RDB5_RRDB) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) ld_global_256_nv(xb + hh * 32 + g * 8, r0[g]);
+        for (int g = 0; g < 4; ++g) ld_global_256_nv(xb + (hh * 4 + g) * TRUNK_GSTRIDE, r0[g]);
       }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -223,18 +234,18 @@ __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* s
           acc[c] = v;
           o[i] = __float_as_uint(v);
         }
-        if constexpr (EPI == EPI_RDB5_RRDB) st_global_256(xb + hh * 32 + g * 8, o);
-        st_global_256(xa + hh * 32 + g * 8, o);
+        if constexpr (EPI == EPI_RDB5_RRDB) st_global_256(xb + (hh * 4 + g) * TRUNK_GSTRIDE, o);
+        st_global_256(xa + (hh * 4 + g) * TRUNK_GSTRIDE, o);
       }
     }
     store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc, a.out_fp16);
   } else if constexpr (EPI == EPI_ADD_F32) {
-    const float* f = a.fadd + pix * COUT;
+    const float* f = a.fadd + trunk_off(n, y, x, a.H, a.W);
 #pragma unroll
     for (int hh = 0; hh < COUT / 32; ++hh) {
       uint32_t r[4][8];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) ld_global_256_nv(f + hh * 32 + g * 8, r[g]);
+      for (int g = 0; g < 4; ++g) ld_global_256_nv(f + (hh * 4 + g) * TRUNK_GSTRIDE, r[g]);
 #pragma unroll
       for (int g = 0; g < 4; ++g)
 #pragma unroll
@@ -455,22 +466,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
       const int x = tx * 128 + m;
       const int y0 = ty * TH;
       if constexpr (EPI == EPI_RDB5 || EPI == EPI_RDB5_RRDB || EPI == EPI_ADD_F32) {
-        // pull this tile's fp32 residual rows towards L2 while the MMAs run
-        if (x < args.W) {
-          for (int Y = eg; Y < TH; Y += NGRP) {
-            const int y = y0 + Y;
-            if (y >= args.H) break;
-            const size_t pix = (static_cast<size_t>(n) * args.H + y) * args.W + x;
+        // pull this tile's fp32 residual rows towards L2 while the MMAs run (each warp: 8 groups x 1 KB per row)
+        for (int Y = eg; Y < TH; Y += NGRP) {
+          const int y = y0 + Y;
+          if (y >= args.H) break;
+          const size_t wbase = trunk_off(n, y, tx * 128 + q * 32, args.H, args.W) + (lane & 7) * 32;
+#pragma unroll
+          for (int t2 = 0; t2 < 2; ++t2) {
+            const size_t o = wbase + static_cast<size_t>(t2 * 4 + (lane >> 3)) * TRUNK_GSTRIDE;
             if constexpr (EPI == EPI_ADD_F32) {
-              prefetch_l2(args.fadd + pix * COUT);
-              prefetch_l2(args.fadd + pix * COUT + 32);
+              prefetch_l2(args.fadd + o);
             } else {
-              prefetch_l2(args.xa + pix * COUT);
-              prefetch_l2(args.xa + pix * COUT + 32);
-              if constexpr (EPI == EPI_RDB5_RRDB) {
-                prefetch_l2(args.xb + pix * COUT);
-                prefetch_l2(args.xb + pix * COUT + 32);
-              }
+              prefetch_l2(args.xa + o);
+              if constexpr (EPI == EPI_RDB5_RRDB) prefetch_l2(args.xb + o);
             }
           }
         }

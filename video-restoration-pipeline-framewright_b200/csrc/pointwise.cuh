@@ -100,13 +100,13 @@ __global__ void __launch_bounds__(128) first_conv_kernel(const FirstArgs a) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     if (f32dst[k]) {
-      float* d = f32dst[k] + pix * 64;
+      float* d = f32dst[k] + trunk_off(n, y, x, a.H, a.W);   // tile-interleaved fp32 trunk layout
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         uint32_t o[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(acc[g * 8 + i]);
-        st_global_256(d + g * 8, o);
+        st_global_256(d + g * TRUNK_GSTRIDE, o);
       }
     }
   }

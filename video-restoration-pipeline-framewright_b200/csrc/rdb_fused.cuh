@@ -1,0 +1,499 @@
+// One persistent kernel per Residual Dense Block: the five 3x3 convs of an RDB
+// (basicsr ResidualDenseBlock.forward; constructed through RRDBNet at
+// /root/reference/src/framewright/processors/pytorch_realesrgan.py:107-127) run as ONE launch so that the
+// dense-block intermediates x1..x4 are produced and consumed while still resident in the 126 MB L2.
+//
+// Why: un-fused, every conv of an RDB re-reads the whole dense buffer from HBM; at 720p that is 1.8 KB of
+// DRAM traffic per pixel per RDB and puts all five convs below the roofline ridge.
+//
+// How: the work is cut into items (conv k, 128-pixel column tx, 16 rows; 8 rows for conv5) and ordered strip by
+// strip: within strip s the items of conv1 come first, then conv2 (shifted UP by 8 rows relative to conv1),
+// conv3 (by 16) ... conv5 (by 32), so everything an item reads from a lower conv is produced by items that
+// precede it in the list, at most ~70 image rows (< 40 MB of bf16) earlier.  Items are dealt round-robin to
+// the resident CTAs; a CTA executes its items in order with the same TMA -> tcgen05 -> epilogue pipeline as
+// conv3x3_tc_kernel (per-item layer parameters).  Cross-CTA dependencies are completion counters per
+// (frame, conv, block of 8 rows) in global memory: epilogue warps release (threadfence + atomicAdd) when
+// their rows of a block are stored; the TMA producer of a consuming item acquires (ld.acquire.gpu +
+// fence.proxy.async) before it loads an input row of the first channel chunk that contains the
+// predecessor's output.  That is the LAST chunk of the item, and the predecessor's rows also complete during
+// ITS last chunk, so producer and consumer items that start together stream row-block by row-block with
+// little waiting.  All CTAs are co-resident (grid <= #SMs, 1 CTA/SM) and dependencies always point to
+// lower-numbered items, so the schedule cannot deadlock.
+#pragma once
+#include "conv3x3_tc.cuh"
+
+namespace b200sr {
+
+struct RdbItem {      // 32 bytes, built on the host (b200sr.cu::build_rdb_items)
+  int k;              // conv index 0..4 (conv1..conv5)
+  int n;              // frame
+  int y0;             // first output row
+  int rows;           // output rows in this item (<= 16 for k < 4, <= 8 for k == 4)
+  int tx;             // 128-pixel column
+  int flag_base;      // index of the completion counter of 8-row block 0 of (n, k); -1 for conv5
+  int dep_base[2];    // per dependent chunk (c = 1, 2): counter base of the conv whose output that chunk needs
+                      // (-1 = none); block b's counter is dep_base + b
+};
+
+struct RdbArgs {
+  ConvArgs L[5];          // per-conv parameters (wpack, bias, nchunks, last_ksteps, out/out_choff, xa/xb, ...)
+  const RdbItem* items;
+  int nitems;
+  int* flags;             // [frame][conv1..4][8-row block], zeroed before the launch
+  int* counter;           // next unclaimed item (zeroed before the launch): items are claimed in list order
+  int flag_target;        // counter value of a complete block: column tiles x epilogue warps
+  int rrdb_end;           // conv5 epilogue also applies the RRDB-level skip
+  long long* stats;       // optional [grid][16] cycle counters (dev tool; nullptr = off)
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// generic -> async proxy ordering for GLOBAL memory only (the unrestricted form also covers shared memory)
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// conv5 tail of one pixel with the fp32 trunk row `xr` already in registers (loaded while the MMAs were still
+// running): x <- (acc + b) * 0.2 + x ; optionally x <- x * 0.2 + x0 and x0 <- x (RRDB end); + bf16 copy.
+template <bool RRDB>
+__device__ __forceinline__ void rdb5_pixel(const ConvArgs& a, const float* s_bias, float (&acc)[64],
+                                           const uint32_t (&xr)[8][8], int n, int y, int x) {
+  const size_t pix = (static_cast<size_t>(n) * a.H + y) * a.W + x;
+  const size_t toff = trunk_off(n, y, x, a.H, a.W);
+  float* xa = a.xa + toff;
+  float* xb = a.xb + toff;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    uint32_t r0[4][8];
+    if constexpr (RRDB) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) ld_global_256_nv(xb + (hh * 4 + g) * TRUNK_GSTRIDE, r0[g]);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = hh * 32 + g * 8 + i;
+        float v = (acc[c] + s_bias[c]) * 0.2f + __uint_as_float(xr[hh * 4 + g][i]);
+        if constexpr (RRDB) v = v * 0.2f + __uint_as_float(r0[g][i]);
+        acc[c] = v;
+        o[i] = __float_as_uint(v);
+      }
+      if constexpr (RRDB) st_global_256(xb + (hh * 4 + g) * TRUNK_GSTRIDE, o);
+      st_global_256(xa + (hh * 4 + g) * TRUNK_GSTRIDE, o);
+    }
+  }
+  store_bf16_row<64>(a.out + pix * a.out_pitch + a.out_choff, acc, 0);
+}
+
+#define RDB_TIMED(slot, ...)                           \
+  do {                                                 \
+    if (st_on) {                                       \
+      const long long t__ = clock64();                 \
+      __VA_ARGS__;                                     \
+      st_acc[slot] += clock64() - t__;                 \
+    } else {                                           \
+      __VA_ARGS__;                                     \
+    }                                                  \
+  } while (0)
+
+constexpr int RDB_QD = 2;
+constexpr int RDB_NSTAGES = 4;
+constexpr int RDB_WBUF_BYTES = 9 * 64 * 128;                 // weight chunk buffer sized for Cout = 64
+constexpr int RDB_A_STAGE_BYTES = 17 * 1024;
+constexpr int RDB_SMEM_BYTES = 2 * RDB_WBUF_BYTES + RDB_NSTAGES * RDB_A_STAGE_BYTES + 1024;
+constexpr int RDB_NEPI_WARPS = 8;
+constexpr int RDB_NTHREADS = 32 * (2 + RDB_NEPI_WARPS);
+
+__global__ void __launch_bounds__(RDB_NTHREADS, 1)
+rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ RdbArgs args) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + 2 * RDB_WBUF_BYTES;
+
+  __shared__ uint64_t bar_full[RDB_NSTAGES], bar_empty[RDB_NSTAGES];
+  __shared__ uint64_t bar_wfull[2], bar_wempty[2];
+  __shared__ uint64_t bar_rfull[16], bar_rempty[16];   // one per 32-column TMEM slot
+  __shared__ uint64_t bar_qfull[RDB_QD], bar_qempty[RDB_QD];   // claimed-item queue: producer -> MMA + epilogue warps
+  __shared__ int s_q[RDB_QD];
+  __shared__ RdbItem s_qitem[RDB_QD];
+  __shared__ uint32_t s_tmem_base;
+  __shared__ float s_bias[5][64];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < 5 * 64; i += blockDim.x) {
+    const int k = i >> 6, c = i & 63;
+    s_bias[k][c] = (k < 4 && c >= 32) ? 0.f : args.L[k].bias[c];
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RDB_NSTAGES; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_wfull[i], 1);
+      mbar_init(&bar_wempty[i], 1);
+    }
+    for (int i = 0; i < 16; ++i) {
+      mbar_init(&bar_rfull[i], 1);
+      mbar_init(&bar_rempty[i], 4);
+    }
+    for (int i = 0; i < RDB_QD; ++i) {
+      mbar_init(&bar_qfull[i], 1);
+      mbar_init(&bar_qempty[i], 1 + RDB_NEPI_WARPS);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&amap);
+  }
+  if (warp == 1) {
+    tmem_alloc(&s_tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+  const bool st_on = args.stats != nullptr;
+  long long st_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long st_t0 = clock64();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    // Items are claimed dynamically, in list order (atomic counter): an item never starts before a lower-numbered
+    // one, so a producer item that precedes its consumer by >= one "round" of CTAs has already finished.
+    int stage = 0, phase = 0, wb = 0, wphase = 0, qi = 0, qphase = 0;
+    // (Claiming an item ahead of time was measured to be much worse: a claimed-but-not-started item delays all its
+    // consumers.  Items are claimed exactly when the producer warp is ready to start them.)
+    while (true) {
+      mbar_wait(&bar_qempty[qi], qphase ^ 1);
+      if (lane == 0) {
+        const int claimed = atomicAdd(args.counter, 1);
+        if (claimed < args.nitems) {
+          s_qitem[qi] = args.items[claimed];
+          s_q[qi] = claimed;
+        } else {
+          s_q[qi] = -1;
+        }
+        mbar_arrive(&bar_qfull[qi]);
+      }
+      __syncwarp();
+      const int it = s_q[qi];
+      const RdbItem item = s_qitem[qi];
+      if (++qi == RDB_QD) {
+        qi = 0;
+        qphase ^= 1;
+      }
+      if (it < 0) break;
+      const ConvArgs& L = args.L[item.k];
+      const int cout = item.k < 4 ? 32 : 64;
+      const uint32_t wtile = 3u * cout * 128u;
+      const int x0 = item.tx * 128 - 1;
+      for (int c = 0; c < L.nchunks; ++c) {
+        RDB_TIMED(2, mbar_wait(&bar_wempty[wb], wphase ^ 1));
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&bar_wfull[wb], 3 * wtile);
+          const uint8_t* wsrc = L.wpack + static_cast<size_t>(c) * 3 * wtile;
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+            bulk_load_1d(&bar_wfull[wb], sW + wb * RDB_WBUF_BYTES + d * wtile, wsrc + d * wtile, wtile);
+        }
+        __syncwarp();
+        // The 8-row blocks of the predecessor conv this chunk reads (rows y0-1 .. y0+rows, at most 4 blocks) must
+        // be complete.  One batch of relaxed loads (the common case: all complete), then ONE acquire fence and
+        // one generic->async proxy fence before the TMA loads of the chunk's rows (the weights, which do not depend
+        // on other CTAs, are already in flight).
+        const int dep = (c > 0) ? item.dep_base[c - 1] : -1;
+        if (dep >= 0) {
+          RDB_TIMED(3 + item.k, {
+            if (elect_one_sync()) {
+              const int bl = (item.y0 > 0 ? item.y0 - 1 : 0) >> 3;
+              const int r_hi = item.y0 + item.rows < L.H ? item.y0 + item.rows : L.H - 1;
+              const int nb = (r_hi >> 3) - bl + 1;
+              const int* f = args.flags + dep + bl;
+              int v[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[j] = j < nb ? ld_relaxed_gpu(f + j) : args.flag_target;
+              while (v[0] < args.flag_target || v[1] < args.flag_target || v[2] < args.flag_target ||
+                     v[3] < args.flag_target) {
+                __nanosleep(64);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (j < nb && v[j] < args.flag_target) v[j] = ld_relaxed_gpu(f + j);
+              }
+              fence_acq_rel_gpu();
+              fence_proxy_async_global();
+            }
+            __syncwarp();
+          });
+        }
+        for (int y = -1; y <= item.rows; ++y) {
+          const int r = item.y0 + y;
+          RDB_TIMED(1, mbar_wait(&bar_empty[stage], phase ^ 1));
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&bar_full[stage], 130 * 128);
+            tma_load_4d(&amap, &bar_full[stage], sA + stage * RDB_A_STAGE_BYTES, c * 64, x0, r, item.n);
+          }
+          __syncwarp();
+          if (++stage == RDB_NSTAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        wb ^= 1;
+        if (wb == 0) wphase ^= 1;
+      }
+    }
+    if (st_on && lane == 0) {
+      long long* o = args.stats + blockIdx.x * 16;
+      o[0] = st_acc[4] + st_acc[5] + st_acc[6] + st_acc[7];
+      o[1] = st_acc[1];
+      o[2] = st_acc[2];
+      o[3] = clock64() - st_t0;
+
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint64_t adesc0 = make_smem_desc(smem_u32(sA), 1024, SWZ_128B, 0);
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(sW), 1024, SWZ_128B, 0);
+    int stage = 0, phase = 0, wb = 0, wphase = 0;
+    uint32_t rempty_par = 0xFFFFu;   // parity to wait for, per 32-column slot (fresh barrier: parity 1 passes)
+    int qi = 0, qphase = 0;
+    while (true) {
+      mbar_wait(&bar_qfull[qi], qphase);
+      const int it = s_q[qi];
+      const RdbItem item = s_qitem[qi];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_qempty[qi]);
+      if (++qi == RDB_QD) {
+        qi = 0;
+        qphase ^= 1;
+      }
+      if (it < 0) break;
+      const ConvArgs& L = args.L[item.k];
+      const int TH = item.rows;
+      const int cout = item.k < 4 ? 32 : 64;
+      const int spr = cout >> 5;   // 32-column slots per accumulator row
+      const uint32_t wtile = 3u * cout * 128u;
+      const uint32_t idesc1 = make_idesc_16(128, cout, false);
+      const uint32_t idesc2 = make_idesc_16(128, 2 * cout, false);
+      const uint32_t idesc3 = make_idesc_16(128, 3 * cout, false);
+      for (int c = 0; c < L.nchunks; ++c) {
+        const int ks = (c == L.nchunks - 1) ? L.last_ksteps : 4;
+        const bool first_chunk = (c == 0);
+        const bool last_chunk = (c == L.nchunks - 1);
+        RDB_TIMED(0, mbar_wait(&bar_wfull[wb], wphase));
+        const uint64_t bdesc_w = bdesc0 + static_cast<uint64_t>((wb * RDB_WBUF_BYTES) >> 4);
+        // Two input rows (two pipeline stages) per burst: the tensor pipe buffers only a couple of instructions, so
+        // every barrier wait / descriptor computation between bursts is a pipe bubble (probe_umma.cu T6: the gap
+        // costs ~150 cycles + ~40-85 per commit regardless of burst length).  24 MMAs per burst halve that cost.
+        for (int y = -1; y <= TH; y += 2) {
+          const int ny = (y + 1 <= TH) ? 2 : 1;
+          uint32_t dcol[2], idn[2], nblk_[2];
+          uint64_t ad0[2], bd0[2];
+          bool newr[2];
+          int stg[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int yy = y + j;
+            const int blk_lo = (yy < 1) ? (1 - yy) : 0;
+            const int blk_hi = (TH - yy < 2) ? (TH - yy) : 2;
+            const int nblk = blk_hi - blk_lo + 1;
+            nblk_[j] = nblk;
+            newr[j] = first_chunk && blk_hi == 2 && j < ny;   // accumulator row yy+1 is touched for the first time
+            stg[j] = (stage + j) & (RDB_NSTAGES - 1);
+            dcol[j] = tmem_base + static_cast<uint32_t>((yy - 1 + blk_lo) * cout);
+            ad0[j] = adesc0 + static_cast<uint64_t>((stg[j] * RDB_A_STAGE_BYTES) >> 4);
+            bd0[j] = bdesc_w + static_cast<uint64_t>((blk_lo * cout * 128) >> 4);
+            idn[j] = nblk == 3 ? idesc3 : (nblk == 2 ? idesc2 : idesc1);
+            if (newr[j]) {
+              for (int sl = (yy + 1) * spr; sl < (yy + 2) * spr; ++sl) {
+                RDB_TIMED(1, mbar_wait(&bar_rempty[sl], (rempty_par >> sl) & 1u));
+                rempty_par ^= 1u << sl;
+              }
+            }
+          }
+          RDB_TIMED(2, mbar_wait(&bar_full[stg[0]], phase));
+          if (ny == 2) RDB_TIMED(2, mbar_wait(&bar_full[stg[1]], stg[1] < stg[0] ? (phase ^ 1) : phase));
+          tc_fence_after();
+          const long long t_issue = st_on ? clock64() : 0;
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              if (j < ny) {
+                if (newr[j]) {
+                  if (nblk_[j] > 1) umma_bf16(dcol[j], ad0[j], bd0[j], nblk_[j] == 3 ? idesc2 : idesc1, 1);
+                  umma_bf16(dcol[j] + (nblk_[j] - 1) * cout, ad0[j],
+                            bd0[j] + static_cast<uint64_t>(((nblk_[j] - 1) * cout * 128) >> 4), idesc1, 0);
+                } else {
+                  umma_bf16(dcol[j], ad0[j], bd0[j], idn[j], 1);
+                }
+                if (ks == 4) {
+#pragma unroll
+                  for (int i = 1; i < 12; ++i) {
+                    const int dx = i >> 2, k = i & 3;
+                    umma_bf16(dcol[j], ad0[j] + static_cast<uint64_t>((dx * 128 + k * 32) >> 4),
+                              bd0[j] + static_cast<uint64_t>((dx * wtile + k * 32) >> 4), idn[j], 1);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 1; i < 6; ++i) {
+                    const int dx = i >> 1, k = i & 1;
+                    umma_bf16(dcol[j], ad0[j] + static_cast<uint64_t>((dx * 128 + k * 32) >> 4),
+                              bd0[j] + static_cast<uint64_t>((dx * wtile + k * 32) >> 4), idn[j], 1);
+                  }
+                }
+                umma_commit(&bar_empty[stg[j]]);
+                const int yy = y + j;
+                if (last_chunk && yy >= 1) umma_commit(&bar_rfull[(yy - 1) * spr]);   // output row yy-1 is complete
+              }
+            }
+            if (y + ny - 1 == TH) umma_commit(&bar_wempty[wb]);
+          }
+          __syncwarp();
+          if (st_on) {
+            st_acc[3] += clock64() - t_issue;
+            st_acc[4] += ny;
+          }
+          stage += ny;
+          if (stage >= RDB_NSTAGES) {
+            stage -= RDB_NSTAGES;
+            phase ^= 1;
+          }
+        }
+        wb ^= 1;
+        if (wb == 0) wphase ^= 1;
+      }
+    }
+    if (st_on && lane == 0) {
+      long long* o = args.stats + blockIdx.x * 16;
+      o[4] = st_acc[0];
+      o[5] = st_acc[1];
+      o[6] = st_acc[2];
+      o[7] = st_acc[3];
+      o[8] = st_acc[4];
+      o[9] = clock64() - st_t0;
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (2..9)
+    const int eg = (warp - 2) >> 2;          // row-parity group
+    const int q = warp & 3;                  // TMEM lane quarter
+    const int m = q * 32 + lane;
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t rfull_par = 0;                  // parity to wait for, per slot
+    int qi = 0, qphase = 0;
+    while (true) {
+      mbar_wait(&bar_qfull[qi], qphase);
+      const int it = s_q[qi];
+      const RdbItem item = s_qitem[qi];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_qempty[qi]);
+      if (++qi == RDB_QD) {
+        qi = 0;
+        qphase ^= 1;
+      }
+      if (it < 0) break;
+      const ConvArgs& L = args.L[item.k];
+      const int n = item.n;
+      const int x = item.tx * 128 + m;
+      if (item.k == 4) {
+        // pull the fp32 residual rows of this item towards L2 while the MMAs run (8 groups x 1 KB per warp-row)
+        for (int Y = eg; Y < item.rows; Y += 2) {
+          const size_t wbase = trunk_off(n, item.y0 + Y, item.tx * 128 + q * 32, L.H, L.W) + (lane & 7) * 32;
+#pragma unroll
+          for (int t2 = 0; t2 < 2; ++t2) {
+            const size_t o = wbase + static_cast<size_t>(t2 * 4 + (lane >> 3)) * TRUNK_GSTRIDE;
+            prefetch_l2(L.xa + o);
+            if (args.rrdb_end) prefetch_l2(L.xb + o);
+          }
+        }
+        for (int Y = 0; Y < item.rows; ++Y) {
+          const int sl = 2 * Y;
+          if ((Y & 1) == eg) {
+            // fetch this pixel's fp32 trunk row now, while the MMAs of the row are still in flight
+            uint32_t xr[8][8];
+            if (x < L.W) {
+              const float* xa = L.xa + trunk_off(n, item.y0 + Y, x, L.H, L.W);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) ld_global_256(xa + g * TRUNK_GSTRIDE, xr[g]);
+            }
+            RDB_TIMED(0, mbar_wait(&bar_rfull[sl], (rfull_par >> sl) & 1u));
+            tc_fence_after();
+            float acc[64];
+            RDB_TIMED(1, load_acc_row<64>(tlane + static_cast<uint32_t>(Y * 64), acc));
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&bar_rempty[sl]);
+              mbar_arrive(&bar_rempty[sl + 1]);
+            }
+            RDB_TIMED(2, {
+              if (x < L.W) {
+                if (args.rrdb_end)
+                  rdb5_pixel<true>(L, s_bias[4], acc, xr, n, item.y0 + Y, x);
+                else
+                  rdb5_pixel<false>(L, s_bias[4], acc, xr, n, item.y0 + Y, x);
+              }
+            });
+            st_acc[3] += 1;
+          }
+          rfull_par ^= 1u << sl;   // every epilogue warp tracks every slot's phase
+        }
+      } else {
+        for (int Y = 0; Y < item.rows; ++Y) {
+          if ((Y & 1) == eg) {
+            RDB_TIMED(0, mbar_wait(&bar_rfull[Y], (rfull_par >> Y) & 1u));
+            tc_fence_after();
+            float acc[32];
+            RDB_TIMED(4, load_acc_row<32>(tlane + static_cast<uint32_t>(Y * 32), acc));
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_rempty[Y]);
+            RDB_TIMED(5, {
+              if (x < L.W) epilogue_pixel<32, EPI_ACT_BF16>(L, s_bias[item.k], s_bias[item.k], acc, n, item.y0 + Y, x);
+            });
+            st_acc[6] += 1;
+          }
+          rfull_par ^= 1u << Y;
+          // publish an 8-row block once this warp has stored its rows of it (item.y0 is a multiple of 8); the
+          // block is complete when every epilogue warp of every column tile has added 1
+          if ((Y & 7) == 7 || Y == item.rows - 1) {
+            RDB_TIMED(7, {
+              __syncwarp();   // orders every lane's stores before lane 0's release (cumulative at gpu scope)
+              if (lane == 0) red_release_gpu_add(args.flags + item.flag_base + ((item.y0 + Y) >> 3), 1);
+            });
+          }
+        }
+      }
+    }
+  }
+
+  if (st_on && warp == 2 && lane == 0) {
+    long long* o = args.stats + blockIdx.x * 16;
+    o[10] = st_acc[0];
+    o[11] = clock64() - st_t0;
+    // epilogue detail reuses the producer's per-conv slots of CTAs' row 12..15 is taken; print via printf-free path:
+    o[12] = st_acc[1];   // conv5: tcgen05.ld
+    o[13] = st_acc[2];   // conv5: math + global
+    o[14] = st_acc[4] + st_acc[5];   // conv1-4: ld + math/global
+    o[15] = st_acc[7] * 1000000 + st_acc[3] * 1000 + st_acc[6];   // release cycles | conv5 rows | conv1-4 rows
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace b200sr

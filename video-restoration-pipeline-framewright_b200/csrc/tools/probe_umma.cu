@@ -333,6 +333,7 @@ t5_kernel(const __grid_constant__ CUtensorMap amap, int niter, int mode, int tma
 // ----------------------------------------------------------------------------- T6
 // MMA bursts as the conv kernel issues them: 12 x (M128 x N96 x K16) then `ncommit` tcgen05.commit to distinct
 // mbarriers; accumulator column offset `col0 + 32 * (burst % nrows)`.
+template <int BURST>
 __global__ void __launch_bounds__(128, 1) t6_kernel(int nburst, int ncommit, int col0, int nrows, long long* cyc_out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -365,9 +366,10 @@ __global__ void __launch_bounds__(128, 1) t6_kernel(int nburst, int ncommit, int
       const uint64_t ad0 = abase + (uint64_t)(((b & 3) * 17408) >> 4);
       if (elect_one_sync()) {
 #pragma unroll
-        for (int i = 0; i < 12; ++i) {
-          const int dx = i >> 2, k = i & 3;
-          umma_bf16(dcol, ad0 + (uint64_t)((dx * 128 + k * 32) >> 4), bbase + (uint64_t)((dx * 12288 + k * 32) >> 4), idesc, 1);
+        for (int i = 0; i < BURST; ++i) {
+          const int st = i / 12, dx = (i % 12) >> 2, k = i & 3;
+          umma_bf16(dcol, ad0 + (uint64_t)((((st + b) & 3) * 17408 - (b & 3) * 17408 + dx * 128 + k * 32) >> 4),
+                    bbase + (uint64_t)((dx * 12288 + k * 32) >> 4), idesc, 1);
         }
         for (int c = 0; c < ncommit; ++c) umma_commit(&bar_c[c]);
       }
@@ -596,20 +598,24 @@ int main(int argc, char** argv) {
   {
     long long* dc;
     CK(cudaMalloc(&dc, 148 * 8));
-    CK(cudaFuncSetAttribute(t6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    const int nburst = 512;
-    struct Cfg { int ncommit, col0, nrows; } cfgs[] = {{0, 0, 1}, {1, 0, 1}, {2, 0, 1}, {3, 0, 1}, {1, 32, 1}, {1, 0, 8}, {1, 32, 12}, {2, 32, 12}};
-    for (auto& c : cfgs) {
+    auto run = [&](auto kern, int burst, int ncommit) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      const int nburst = 6144 / burst;
       for (int rep = 0; rep < 2; ++rep) {
-        t6_kernel<<<148, 128, 200 * 1024>>>(nburst, c.ncommit, c.col0, c.nrows, dc);
+        kern<<<148, 128, 200 * 1024>>>(nburst, ncommit, 32, 12, dc);
         CK(cudaDeviceSynchronize());
       }
       std::vector<long long> hc(148);
       CK(cudaMemcpy(hc.data(), dc, 148 * 8, cudaMemcpyDeviceToHost));
       long long mx = 0;
       for (auto v : hc) mx = v > mx ? v : mx;
-      printf("T6 bursts of 12 x N96, commits/burst=%d col0=%d rows=%d : %.1f cyc/mma\n", c.ncommit, c.col0, c.nrows,
-             (double)mx / (nburst * 12));
+      printf("T6 bursts of %2d x N96, commits/burst=%d : %.1f cyc/mma (%.0f cyc overhead per burst)\n", burst, ncommit,
+             (double)mx / (nburst * burst), (double)mx / nburst - 56.1 * burst);
+    };
+    for (int nc : {0, 1, 2, 4}) {
+      run(t6_kernel<12>, 12, nc);
+      run(t6_kernel<24>, 24, nc);
+      run(t6_kernel<48>, 48, nc);
     }
     cudaFree(dc);
   }
