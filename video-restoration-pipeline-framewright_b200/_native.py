@@ -69,7 +69,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise NativeLibraryError("nvcc not found; cannot build libb200sr.so")
     tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp, os.path.join(CSRC_DIR, "b200sr.cu")]
+    extra = os.environ.get("B200SR_EXTRA_NVCC_FLAGS", "").split()   # e.g. -DB200SR_RDB_STATS for tools/rdb_stats.py
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", tmp, os.path.join(CSRC_DIR, "b200sr.cu")]
     if verbose:
         print(" ".join(cmd))
     proc = subprocess.run(cmd, capture_output=True, text=True)

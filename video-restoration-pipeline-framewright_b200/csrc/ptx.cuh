@@ -56,6 +56,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Warp-converged wait: one lane polls (sleeping in hardware between probes), the other 31 park at the warp
+// barrier instead of all spinning on the same mbarrier (less issue-slot and power waste).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+
 // ----------------------------------------------------------------------- TMA
 // 4-D tiled tensor load (coords innermost first), completion on an mbarrier.
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,

@@ -97,6 +97,10 @@ __device__ __forceinline__ void rdb5_pixel(const ConvArgs& a, const float* s_bia
   store_bf16_row<64>(a.out + pix * a.out_pitch + a.out_choff, acc, 0);
 }
 
+// Dev instrumentation (per-role wait / issue cycle counters, tools/rdb_stats.py): compiled in only with
+// -DB200SR_RDB_STATS.  It costs registers and local-memory traffic, so product builds leave it out.
+#ifdef B200SR_RDB_STATS
+#define RDB_STATS_ON 1
 #define RDB_TIMED(slot, ...)                           \
   do {                                                 \
     if (st_on) {                                       \
@@ -107,6 +111,17 @@ __device__ __forceinline__ void rdb5_pixel(const ConvArgs& a, const float* s_bia
       __VA_ARGS__;                                     \
     }                                                  \
   } while (0)
+#define RDB_COUNT(slot, v) st_acc[slot] += (v)
+#else
+#define RDB_STATS_ON 0
+#define RDB_TIMED(slot, ...) \
+  do {                       \
+    __VA_ARGS__;             \
+  } while (0)
+#define RDB_COUNT(slot, v) \
+  do {                     \
+  } while (0)
+#endif
 
 constexpr int RDB_QD = 2;
 constexpr int RDB_NSTAGES = 4;
@@ -167,9 +182,9 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
-  const bool st_on = args.stats != nullptr;
+  const bool st_on = RDB_STATS_ON && args.stats != nullptr;
   long long st_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const long long st_t0 = clock64();
+  const long long st_t0 = st_on ? clock64() : 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -365,8 +380,8 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
           }
           __syncwarp();
           if (st_on) {
-            st_acc[3] += clock64() - t_issue;
-            st_acc[4] += ny;
+            RDB_COUNT(3, clock64() - t_issue);
+            RDB_COUNT(4, ny);
           }
           stage += ny;
           if (stage >= RDB_NSTAGES) {
@@ -448,7 +463,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
                   rdb5_pixel<false>(L, s_bias[4], acc, xr, n, item.y0 + Y, x);
               }
             });
-            st_acc[3] += 1;
+            RDB_COUNT(3, 1);
           }
           rfull_par ^= 1u << sl;   // every epilogue warp tracks every slot's phase
         }
@@ -465,7 +480,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             RDB_TIMED(5, {
               if (x < L.W) epilogue_pixel<32, EPI_ACT_BF16>(L, s_bias[item.k], s_bias[item.k], acc, n, item.y0 + Y, x);
             });
-            st_acc[6] += 1;
+            RDB_COUNT(6, 1);
           }
           rfull_par ^= 1u << Y;
           // publish an 8-row block once this warp has stored its rows of it (item.y0 is a multiple of 8); the
