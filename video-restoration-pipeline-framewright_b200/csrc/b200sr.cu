@@ -349,6 +349,7 @@ int ensure_ws(b200sr_engine* e, size_t bytes, cudaStream_t st) {
 
 // ---- fused RDB: item table (skewed row strips) ------------------------------------------------------
 constexpr int RDB_STRIP = 16;   // rows per strip (= rows per conv1..4 item; conv5 items have 8)
+int RDB_ORDER[5] = {0, 1, 2, 3, 4};      // order of the convs inside one step of the work list (option rdb_order)
 int RDB_STEP_OFF[5] = {0, 1, 2, 3, 5};   // step in which conv k reaches strip s: s + RDB_STEP_OFF[k] (option rdb_off)
 
 // Strip s of conv k covers rows [16 s - 8 k, 16 s + 16 - 8 k): every conv is shifted up by 8 rows relative to
@@ -361,7 +362,9 @@ void build_rdb_items(int N, int H, int W, std::vector<RdbItem>& items, int* nfla
   items.clear();
   for (int n = 0; n < N; ++n)
     for (int t = 0; t < S + RDB_STEP_OFF[4]; ++t)
-      for (int k = 0; k < 5; ++k) {
+      for (int kk = 0; kk < 5; ++kk) {
+        // within a step all groups are independent; the natural order conv1..conv5 measured best (rdb_sweep.py)
+        const int k = RDB_ORDER[kk];
         // in step t conv k works on strip t - RDB_STEP_OFF[k]: its producer ran one or two steps (~60 items each)
         // earlier.  conv5 trails conv4 by two steps: conv4 items are the longest and finish their rows last,
         // conv5 items are short and reach their dependent chunk early.
@@ -947,6 +950,15 @@ int b200sr_set_option(b200sr_engine* e, const char* key, int value) {
     RDB_STEP_OFF[3] = (value / 10000) % 100;
     RDB_STEP_OFF[4] = (value / 1000000) % 100;
     e->rdb_n = 0;   // rebuild the work list
+    return B200SR_OK;
+  }
+  if (!strcmp(key, "rdb_order")) {   // five decimal digits, e.g. 32104
+    int v = value;
+    for (int i = 4; i >= 0; --i) {
+      RDB_ORDER[i] = v % 10;
+      v /= 10;
+    }
+    e->rdb_n = 0;
     return B200SR_OK;
   }
   if (!strcmp(key, "rdb_stats")) {

@@ -233,7 +233,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
         // on other CTAs, are already in flight).
         const int dep = (c > 0) ? item.dep_base[c - 1] : -1;
         if (dep >= 0) {
-          RDB_TIMED(3 + item.k, {
+          RDB_TIMED(4, {
             if (elect_one_sync()) {
               const int bl = (item.y0 > 0 ? item.y0 - 1 : 0) >> 3;
               const int r_hi = item.y0 + item.rows < L.H ? item.y0 + item.rows : L.H - 1;
@@ -274,7 +274,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
     }
     if (st_on && lane == 0) {
       long long* o = args.stats + blockIdx.x * 16;
-      o[0] = st_acc[4] + st_acc[5] + st_acc[6] + st_acc[7];
+      o[0] = st_acc[4];
       o[1] = st_acc[1];
       o[2] = st_acc[2];
       o[3] = clock64() - st_t0;
