@@ -95,6 +95,9 @@ int b200sr_get_profile(b200sr_engine* e, int nclass, double* ms, double* flops, 
 /* Dev tool: wait / issue cycle counters of the last fused-RDB launch, 16 long long per CTA (needs option
  * "rdb_stats" = 1).  Returns the number of CTAs written. */
 int b200sr_debug_rdb_stats(b200sr_engine* e, long long* out, int max_ctas);
+/* Dev tool: per-item globaltimer stamps of the traced launch (library built with -DB200SR_RDB_STATS), 10 per item:
+ * claim, dep1 begin/end, dep2 begin/end, loads issued, MMAs issued, epilogue done, CTA, unused. */
+int b200sr_debug_rdb_trace(b200sr_engine* e, long long* out, int max_items);
 
 /* Host-only test hooks (no GPU needed).
  * plan_regions: the regions one enhance call is split into (tile == 0: one region; else upstream

@@ -19,11 +19,18 @@ def _q(t: torch.Tensor, dtype) -> torch.Tensor:
 
 def emulate_rrdb(sd: Dict[str, torch.Tensor], img_bgr_u8: np.ndarray, scale: int = 4, num_block: int = 23,
                  act_dtype=torch.bfloat16, w_dtype=torch.bfloat16, trunk_copy_dtype="same", tail_dtype="same",
-                 first_dtype="same", tail_w_dtype="same") -> np.ndarray:
+                 first_dtype="same", tail_w_dtype="same", trunk_mode="f32") -> np.ndarray:
     trunk_copy_dtype = act_dtype if trunk_copy_dtype == "same" else trunk_copy_dtype
     tail_dtype = act_dtype if tail_dtype == "same" else tail_dtype
     first_dtype = act_dtype if first_dtype == "same" else first_dtype
     tail_w_dtype = w_dtype if tail_w_dtype == "same" else tail_w_dtype
+
+    def tq(v):
+        """Residual-stream storage: fp32, a bf16 hi + bf16 lo pair (hi is the conv-input copy), or bf16 alone."""
+        if trunk_mode == "f32":
+            return v
+        hi = _q(v, torch.bfloat16)
+        return hi if trunk_mode == "bf16" else hi + _q(v - hi, torch.bfloat16)
 
     def conv(x, name, wq=True, wd="trunk"):
         w = sd[name + ".weight"].float()
@@ -36,7 +43,7 @@ def emulate_rrdb(sd: Dict[str, torch.Tensor], img_bgr_u8: np.ndarray, scale: int
         from oracle.oracle import pixel_unshuffle
         x = pixel_unshuffle(x, 2)
     feat = conv(x, "conv_first", wq=False)           # fp32 CUDA-core kernel
-    trunk = feat.clone()
+    trunk = tq(feat.clone())
     xq = _q(feat, first_dtype)
     for b in range(num_block):
         x0 = trunk.clone()
@@ -50,7 +57,7 @@ def emulate_rrdb(sd: Dict[str, torch.Tensor], img_bgr_u8: np.ndarray, scale: int
             x5 = conv(cat, p + "conv5")
             v = x5 * 0.2 + trunk
             # RRDB-level skip fused in the rdb3 epilogue: x <- ((acc+b)*0.2 + x)*0.2 + x0
-            trunk = v * 0.2 + x0 if r == 3 else v
+            trunk = tq(v * 0.2 + x0 if r == 3 else v)
     body = conv(_q(trunk, trunk_copy_dtype), "conv_body")
     feat = _q(feat + body, tail_dtype)
     feat = _q(F.leaky_relu(conv(F.interpolate(feat, scale_factor=2, mode="nearest"), "conv_up1", wd="tail"), 0.2), tail_dtype)

@@ -84,6 +84,8 @@ struct b200sr_engine {
   int opt_rdb_stats = 0;    // dev: collect per-CTA cycle counters of the k-th fused launch of a forward pass (1-based)
   int rdb_launch_idx = 0;
   long long* d_rdb_stats = nullptr;
+  long long* d_rdb_trace = nullptr;
+  long long* d_rdb_trace2 = nullptr;
   // fused-RDB item table (depends only on N, H, W)
   int rdb_n = 0, rdb_h = 0, rdb_w = 0, rdb_nitems = 0, rdb_nflags = 0;
   RdbItem* d_rdb_items = nullptr;
@@ -456,6 +458,12 @@ int launch_rdb_fused(b200sr_engine* e, int li, bool rrdb_end, __nv_bfloat16* Dcu
   if (++e->rdb_launch_idx == e->opt_rdb_stats) {
     if (!e->d_rdb_stats) CUDA_TRY(e, cudaMalloc(&e->d_rdb_stats, 148 * 16 * sizeof(long long)));
     a.stats = e->d_rdb_stats;
+    if (!e->d_rdb_trace) CUDA_TRY(e, cudaMalloc(&e->d_rdb_trace, static_cast<size_t>(e->rdb_nitems) * 10 * sizeof(long long)));
+    CUDA_TRY(e, cudaMemsetAsync(e->d_rdb_trace, 0, static_cast<size_t>(e->rdb_nitems) * 10 * sizeof(long long), st));
+    a.trace = e->d_rdb_trace;
+    if (!e->d_rdb_trace2) CUDA_TRY(e, cudaMalloc(&e->d_rdb_trace2, static_cast<size_t>(e->rdb_nitems) * 48 * sizeof(long long)));
+    CUDA_TRY(e, cudaMemsetAsync(e->d_rdb_trace2, 0, static_cast<size_t>(e->rdb_nitems) * 48 * sizeof(long long), st));
+    a.trace2 = e->d_rdb_trace2;
   }
   static bool attr_done[16] = {};
   if (!attr_done[e->device & 15]) {
@@ -778,6 +786,8 @@ void b200sr_destroy(b200sr_engine* e) {
   if (e->d_rdb_items) cudaFree(e->d_rdb_items);
   if (e->d_rdb_flags) cudaFree(e->d_rdb_flags);
   if (e->d_rdb_stats) cudaFree(e->d_rdb_stats);
+  if (e->d_rdb_trace) cudaFree(e->d_rdb_trace);
+  if (e->d_rdb_trace2) cudaFree(e->d_rdb_trace2);
   if (e->stage_in) cudaFree(e->stage_in);
   if (e->stage_out) cudaFree(e->stage_out);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -1003,6 +1013,18 @@ int b200sr_debug_rdb_stats(b200sr_engine* e, long long* out, int max_ctas) {
   const int n = std::min(max_ctas, std::min(e->num_sms, 148));
   if (cudaMemcpy(out, e->d_rdb_stats, static_cast<size_t>(n) * 16 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return n;
+}
+
+// Dev tool: per-item timestamps of the traced fused-RDB launch; [nitems][10] long long.  Returns nitems.
+int b200sr_debug_rdb_trace(b200sr_engine* e, long long* out, int max_items) {
+  if (!e || !e->d_rdb_trace) return -1;
+  const int n = std::min(std::abs(max_items), e->rdb_nitems);
+  if (max_items < 0) {   // negative count: fetch the per-row trace ([nitems][16][3]) instead
+    if (out && cudaMemcpy(out, e->d_rdb_trace2, static_cast<size_t>(n) * 48 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return e->rdb_nitems;
+  }
+  if (out && cudaMemcpy(out, e->d_rdb_trace, static_cast<size_t>(n) * 10 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return e->rdb_nitems;
 }
 
 // ---- test hooks that need no GPU ----------------------------------------------------------------

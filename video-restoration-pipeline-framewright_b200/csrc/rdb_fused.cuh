@@ -22,6 +22,14 @@
 #pragma once
 #include "conv3x3_tc.cuh"
 
+// timing ablations (tools only; results are wrong when set): skip the epilogue math + stores / the dependency waits
+#ifndef B200SR_ABL_NOEPI
+#define B200SR_ABL_NOEPI 0
+#endif
+#ifndef B200SR_ABL_NODEP
+#define B200SR_ABL_NODEP 0
+#endif
+
 namespace b200sr {
 
 struct RdbItem {      // 32 bytes, built on the host (b200sr.cu::build_rdb_items)
@@ -44,6 +52,8 @@ struct RdbArgs {
   int flag_target;        // counter value of a complete block: column tiles x epilogue warps
   int rrdb_end;           // conv5 epilogue also applies the RRDB-level skip
   long long* stats;       // optional [grid][16] cycle counters (dev tool; nullptr = off)
+  long long* trace;       // optional [nitems][10] globaltimer stamps per item (dev tool; nullptr = off)
+  long long* trace2;      // optional [nitems][16][3] per-row stamps: MMA commit, epilogue wait passed, row stored
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -112,7 +122,29 @@ __device__ __forceinline__ void rdb5_pixel(const ConvArgs& a, const float* s_bia
     }                                                  \
   } while (0)
 #define RDB_COUNT(slot, v) st_acc[slot] += (v)
+#define RDB_STAMP(it, slot)                                                   \
+  do {                                                                        \
+    if (args.trace != nullptr && (threadIdx.x & 31) == 0) {                   \
+      unsigned long long t__;                                                 \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                 \
+      args.trace[static_cast<size_t>(it) * 10 + (slot)] = (long long)t__;    \
+    }                                                                         \
+  } while (0)
+#define RDB_STAMP2(it, row, slot)                                                        \
+  do {                                                                                   \
+    if (args.trace2 != nullptr) {                                                        \
+      unsigned long long t__;                                                            \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                            \
+      args.trace2[(static_cast<size_t>(it) * 16 + (row)) * 3 + (slot)] = (long long)t__; \
+    }                                                                                    \
+  } while (0)
 #else
+#define RDB_STAMP2(it, row, slot) \
+  do {                            \
+  } while (0)
+#define RDB_STAMP(it, slot) \
+  do {                      \
+  } while (0)
 #define RDB_STATS_ON 0
 #define RDB_TIMED(slot, ...) \
   do {                       \
@@ -213,6 +245,10 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
         qphase ^= 1;
       }
       if (it < 0) break;
+      RDB_STAMP(it, 0);
+#ifdef B200SR_RDB_STATS
+      if (args.trace != nullptr && lane == 0) args.trace[static_cast<size_t>(it) * 10 + 8] = blockIdx.x;
+#endif
       const ConvArgs& L = args.L[item.k];
       const int cout = item.k < 4 ? 32 : 64;
       const uint32_t wtile = 3u * cout * 128u;
@@ -232,7 +268,8 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
         // one generic->async proxy fence before the TMA loads of the chunk's rows (the weights, which do not depend
         // on other CTAs, are already in flight).
         const int dep = (c > 0) ? item.dep_base[c - 1] : -1;
-        if (dep >= 0) {
+        if (dep >= 0 && !B200SR_ABL_NODEP) {
+          RDB_STAMP(it, 2 * c - 1);
           RDB_TIMED(4, {
             if (elect_one_sync()) {
               const int bl = (item.y0 > 0 ? item.y0 - 1 : 0) >> 3;
@@ -254,6 +291,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             }
             __syncwarp();
           });
+          RDB_STAMP(it, 2 * c);
         }
         for (int y = -1; y <= item.rows; ++y) {
           const int r = item.y0 + y;
@@ -271,6 +309,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
         wb ^= 1;
         if (wb == 0) wphase ^= 1;
       }
+      RDB_STAMP(it, 5);
     }
     if (st_on && lane == 0) {
       long long* o = args.stats + blockIdx.x * 16;
@@ -298,6 +337,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
         qphase ^= 1;
       }
       if (it < 0) break;
+      RDB_STAMP(it, 9);
       const ConvArgs& L = args.L[item.k];
       const int TH = item.rows;
       const int cout = item.k < 4 ? 32 : 64;
@@ -315,8 +355,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
         // Two input rows (two pipeline stages) per burst: the tensor pipe buffers only a couple of instructions, so
         // every barrier wait / descriptor computation between bursts is a pipe bubble (probe_umma.cu T6: the gap
         // costs ~150 cycles + ~40-85 per commit regardless of burst length).  24 MMAs per burst halve that cost.
-        for (int y = -1; y <= TH; y += 2) {
-          const int ny = (y + 1 <= TH) ? 2 : 1;
+        auto burst = [&](const int y, const int ny) {
           uint32_t dcol[2], idn[2], nblk_[2];
           uint64_t ad0[2], bd0[2];
           bool newr[2];
@@ -373,7 +412,10 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
                 }
                 umma_commit(&bar_empty[stg[j]]);
                 const int yy = y + j;
-                if (last_chunk && yy >= 1) umma_commit(&bar_rfull[(yy - 1) * spr]);   // output row yy-1 is complete
+                if (last_chunk && yy >= 1) {
+                  umma_commit(&bar_rfull[(yy - 1) * spr]);   // output row yy-1 is complete
+                  RDB_STAMP2(it, yy - 1, 0);
+                }
               }
             }
             if (y + ny - 1 == TH) umma_commit(&bar_wempty[wb]);
@@ -388,10 +430,70 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             stage -= RDB_NSTAGES;
             phase ^= 1;
           }
+        };
+        // Row schedule of one chunk: (-1, 0) general; interior pairs through the lean path (rows 1 .. TH-2 feed three
+        // full accumulator rows each: N = 3*cout, no edge cases); the last rows through the general path again.
+        burst(-1, 2);
+        int y = 1;
+        for (; y + 1 <= TH - 2; y += 2) {
+          const int s0 = stage, s1 = (stage + 1) & (RDB_NSTAGES - 1);
+          if (first_chunk) {   // accumulator rows y+1 and y+2 are touched for the first time
+            for (int sl = (y + 1) * spr; sl < (y + 3) * spr; ++sl) {
+              RDB_TIMED(1, mbar_wait(&bar_rempty[sl], (rempty_par >> sl) & 1u));
+              rempty_par ^= 1u << sl;
+            }
+          }
+          RDB_TIMED(2, mbar_wait(&bar_full[s0], phase));
+          RDB_TIMED(2, mbar_wait(&bar_full[s1], s1 < s0 ? (phase ^ 1) : phase));
+          tc_fence_after();
+          const uint32_t dc0 = tmem_base + static_cast<uint32_t>((y - 1) * cout);
+          const uint64_t a0 = adesc0 + static_cast<uint64_t>((s0 * RDB_A_STAGE_BYTES) >> 4);
+          const uint64_t a1 = adesc0 + static_cast<uint64_t>((s1 * RDB_A_STAGE_BYTES) >> 4);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint32_t dc = dc0 + j * cout;
+              const uint64_t ad = j ? a1 : a0;
+              if (first_chunk) {
+                umma_bf16(dc, ad, bdesc_w, idesc2, 1);
+                umma_bf16(dc + 2 * cout, ad, bdesc_w + static_cast<uint64_t>((2 * cout * 128) >> 4), idesc1, 0);
+              } else {
+                umma_bf16(dc, ad, bdesc_w, idesc3, 1);
+              }
+              if (ks == 4) {
+#pragma unroll
+                for (int i = 1; i < 12; ++i) {
+                  const int dx = i >> 2, k = i & 3;
+                  umma_bf16(dc, ad + static_cast<uint64_t>((dx * 128 + k * 32) >> 4),
+                            bdesc_w + static_cast<uint64_t>((dx * wtile + k * 32) >> 4), idesc3, 1);
+                }
+              } else {
+#pragma unroll
+                for (int i = 1; i < 6; ++i) {
+                  const int dx = i >> 1, k = i & 1;
+                  umma_bf16(dc, ad + static_cast<uint64_t>((dx * 128 + k * 32) >> 4),
+                            bdesc_w + static_cast<uint64_t>((dx * wtile + k * 32) >> 4), idesc3, 1);
+                }
+              }
+              umma_commit(&bar_empty[j ? s1 : s0]);
+              if (last_chunk) {
+                umma_commit(&bar_rfull[(y + j - 1) * spr]);   // output row y+j-1 is complete
+                RDB_STAMP2(it, y + j - 1, 0);
+              }
+            }
+          }
+          __syncwarp();
+          stage += 2;
+          if (stage >= RDB_NSTAGES) {
+            stage -= RDB_NSTAGES;
+            phase ^= 1;
+          }
         }
+        for (; y <= TH; y += 2) burst(y, (y + 1 <= TH) ? 2 : 1);
         wb ^= 1;
         if (wb == 0) wphase ^= 1;
       }
+      RDB_STAMP(it, 6);
     }
     if (st_on && lane == 0) {
       long long* o = args.stats + blockIdx.x * 16;
@@ -446,6 +548,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
               for (int g = 0; g < 8; ++g) ld_global_256(xa + g * TRUNK_GSTRIDE, xr[g]);
             }
             RDB_TIMED(0, mbar_wait(&bar_rfull[sl], (rfull_par >> sl) & 1u));
+            if (q == 2 && lane == 0) RDB_STAMP2(it, Y, 1);
             tc_fence_after();
             float acc[64];
             RDB_TIMED(1, load_acc_row<64>(tlane + static_cast<uint32_t>(Y * 64), acc));
@@ -456,7 +559,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
               mbar_arrive(&bar_rempty[sl + 1]);
             }
             RDB_TIMED(2, {
-              if (x < L.W) {
+              if (x < L.W && !(B200SR_ABL_NOEPI & 2)) {
                 if (args.rrdb_end)
                   rdb5_pixel<true>(L, s_bias[4], acc, xr, n, item.y0 + Y, x);
                 else
@@ -464,6 +567,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
               }
             });
             RDB_COUNT(3, 1);
+            if (q == 2 && lane == 0) RDB_STAMP2(it, Y, 2);
           }
           rfull_par ^= 1u << sl;   // every epilogue warp tracks every slot's phase
         }
@@ -471,6 +575,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
         for (int Y = 0; Y < item.rows; ++Y) {
           if ((Y & 1) == eg) {
             RDB_TIMED(0, mbar_wait(&bar_rfull[Y], (rfull_par >> Y) & 1u));
+            if (q == 2 && lane == 0) RDB_STAMP2(it, Y, 1);
             tc_fence_after();
             float acc[32];
             RDB_TIMED(4, load_acc_row<32>(tlane + static_cast<uint32_t>(Y * 32), acc));
@@ -478,9 +583,11 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_rempty[Y]);
             RDB_TIMED(5, {
-              if (x < L.W) epilogue_pixel<32, EPI_ACT_BF16>(L, s_bias[item.k], s_bias[item.k], acc, n, item.y0 + Y, x);
+              if (x < L.W && !(B200SR_ABL_NOEPI & 1))
+                epilogue_pixel<32, EPI_ACT_BF16>(L, s_bias[item.k], s_bias[item.k], acc, n, item.y0 + Y, x);
             });
             RDB_COUNT(6, 1);
+            if (q == 2 && lane == 0) RDB_STAMP2(it, Y, 2);
           }
           rfull_par ^= 1u << Y;
           // publish an 8-row block once this warp has stored its rows of it (item.y0 is a multiple of 8); the
@@ -493,6 +600,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
           }
         }
       }
+      if (warp == 2) RDB_STAMP(it, 7);
     }
   }
 

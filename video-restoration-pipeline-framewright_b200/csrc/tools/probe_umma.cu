@@ -12,6 +12,7 @@
 #include <cuda_bf16.h>
 #include "../ptx.cuh"
 #include "../tmap.h"
+#include "../conv3x3_tc.cuh"
 
 using namespace b200sr;
 
@@ -388,6 +389,151 @@ __global__ void __launch_bounds__(128, 1) t6_kernel(int nburst, int ncommit, int
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+
+// ----------------------------------------------------------------------------- T7
+// TMA activation-box pipeline: `depth` boxes [130 px][64 ch] in flight per SM, lean issue loop (coordinates
+// advance by adds only).  Reports cycles per box and the latency of a single box (depth 1).
+template <int DEPTH>
+__global__ void __launch_bounds__(32, 1)
+t7_kernel(const __grid_constant__ CUtensorMap amap, int niter, int H, int ystride, long long* cyc_out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar[DEPTH];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < DEPTH; ++i) mbar_init(&bar[i], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    int y = (blockIdx.x * 37) % H;
+    const int x = (blockIdx.x % 10) * 128 - 1;
+    int c = 0;
+    uint32_t par = 0;
+    long long t0 = clock64();
+    for (int it = 0; it < niter; it += DEPTH) {
+#pragma unroll
+      for (int s = 0; s < DEPTH; ++s) {
+        if (it > 0) mbar_wait(&bar[s], par ^ 1);
+        mbar_arrive_expect_tx(&bar[s], 130 * 128);
+        tma_load_4d(&amap, &bar[s], smem + s * 17408, c, x, y, 0);
+        y += ystride;
+        if (y >= H) y -= H;
+      }
+      par ^= 1;
+    }
+#pragma unroll
+    for (int s = 0; s < DEPTH; ++s) mbar_wait(&bar[s], par ^ 1);
+    long long t1 = clock64();
+    cyc_out[blockIdx.x] = t1 - t0;
+  }
+}
+template <int DEPTH>
+static void run_t7(const CUtensorMap& amap, int H, int ystride, const char* what, long long* dc) {
+  CK(cudaFuncSetAttribute(t7_kernel<DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  const int niter = 1536;
+  for (int rep = 0; rep < 2; ++rep) {
+    t7_kernel<DEPTH><<<148, 32, 220 * 1024>>>(amap, niter, H, ystride, dc);
+    CK(cudaDeviceSynchronize());
+  }
+  std::vector<long long> hc(148);
+  CK(cudaMemcpy(hc.data(), dc, 148 * 8, cudaMemcpyDeviceToHost));
+  long long mx = 0;
+  double mean = 0;
+  for (auto v : hc) { mx = v > mx ? v : mx; mean += v / 148.0; }
+  printf("T7 %-22s depth=%2d : %.0f cyc/box (mean %.0f) -> %.1f B/cyc/SM, chip %.2f TB/s @1.7GHz\n", what, DEPTH,
+         (double)mx / niter, mean / niter, 16640.0 * niter / mx, 16640.0 * niter / mean * 148 * 1.7e9 / 1e12);
+}
+
+
+// ----------------------------------------------------------------------------- T8
+// How far can the issuing thread run ahead of the tensor pipe?  Issue `n` back-to-back MMAs (N = 96), record the
+// time when issue returns and when the commit fires.
+__global__ void __launch_bounds__(128, 1) t8_kernel(int n, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_done;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (100 * 1024) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + (i & 0xff);
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 96);
+    const uint64_t abase = make_smem_desc(smem_u32(smem), 1024, SWZ_128B, 0);
+    const uint64_t bbase = make_smem_desc(smem_u32(smem) + 4 * 17408, 1024, SWZ_128B, 0);
+    long long t0 = clock64();
+    for (int it = 0; it < n; it += 12) {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        const uint32_t aoff = ((j & 3) * 17408 + (j % 3) * 128 + ((j >> 2) & 3) * 32) >> 4;
+        umma_bf16(tmem + 128, abase + aoff, bbase + (((j >> 2) & 3) * 32 >> 4), idesc, 1);
+      }
+    }
+    long long t1 = clock64();
+    umma_commit(&bar_done);
+    mbar_wait(&bar_done, 0);
+    long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+
+// ----------------------------------------------------------------------------- T9
+// Epilogue store patterns: 8 warps per CTA each store `rows` rows of 32 pixels (NHWC, 384 B pixel pitch).
+//  mode 0: lane = pixel, 2 x 32 B per lane (64 B slice)           -> 2 instr, 32 lines each
+//  mode 1: lane pair = pixel (64 B contiguous per pair)           -> 2 instr, 16 lines each
+//  mode 2: fully contiguous 1 KB per instruction (reference)      -> 2 instr
+//  mode 3: lane = pixel, 4 x 32 B per lane (128 B slice, conv5)   -> 4 instr, 32 lines each
+//  mode 4: 4 lanes = pixel (one full 128 B line per 4 lanes)      -> 4 instr, 8 lines each
+__global__ void __launch_bounds__(256, 1) t9_kernel(uint8_t* out, int rows, int mode, long long* cyc_out, int wrap, int nwarps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t warp_base = ((size_t)blockIdx.x * 8 + warp) * (size_t)wrap * 32 * 384;
+  if (warp >= nwarps) rows = 0;
+  uint32_t v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = threadIdx.x * 8 + i;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int r = 0; r < rows; ++r) {
+    uint8_t* rowp = out + warp_base + (size_t)(r % wrap) * 32 * 384;
+    if (mode == 0) {
+      st_global_256(rowp + lane * 384, v);
+      st_global_256(rowp + lane * 384 + 32, v);
+    } else if (mode == 1) {
+      st_global_256(rowp + (lane >> 1) * 384 + (lane & 1) * 32, v);
+      st_global_256(rowp + (16 + (lane >> 1)) * 384 + (lane & 1) * 32, v);
+    } else if (mode == 2) {
+      st_global_256(rowp + lane * 32, v);
+      st_global_256(rowp + 1024 + lane * 32, v);
+    } else if (mode == 3) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st_global_256(rowp + lane * 384 + j * 32, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st_global_256(rowp + (j * 8 + (lane >> 2)) * 384 + (lane & 3) * 32, v);
+    }
+  }
+  long long t1 = clock64();
+  __syncthreads();
+  if (threadIdx.x == 0) cyc_out[blockIdx.x] = t1 - t0;
+}
+
 int main(int argc, char** argv) {
   int dev = 0;
   CK(cudaSetDevice(dev));
@@ -595,7 +741,7 @@ int main(int argc, char** argv) {
     cudaFree(sink);
   }
   // ------------------------------ T6
-  {
+  if (getenv("PROBE_ALL")) {
     long long* dc;
     CK(cudaMalloc(&dc, 148 * 8));
     auto run = [&](auto kern, int burst, int ncommit) {
@@ -617,6 +763,78 @@ int main(int argc, char** argv) {
       run(t6_kernel<24>, 24, nc);
       run(t6_kernel<48>, 48, nc);
     }
+    cudaFree(dc);
+  }
+  // ------------------------------ T7
+  if (getenv("PROBE_ALL")) {
+    long long* dc;
+    CK(cudaMalloc(&dc, 148 * 8));
+    for (int big = 0; big < 2; ++big) {
+      const int W = 1280, H = big ? 2880 : 64, C = 192;   // 64 rows = 31 MB (L2 resident), 2880 rows = 1.4 GB (DRAM)
+      __nv_bfloat16* dx;
+      CK(cudaMalloc(&dx, (size_t)H * W * C * 2));
+      CK(cudaMemset(dx, 0, (size_t)H * W * C * 2));
+      CUtensorMap amap;
+      if (tmap_encode_act(&amap, dx, 1, H, W, C, 64, 130, 128)) {
+        const char* what = big ? "DRAM (1.4 GB tensor)" : "L2 (31 MB tensor)";
+        const int ys = big ? 19 : 1;
+        run_t7<1>(amap, H, ys, what, dc);
+        run_t7<2>(amap, H, ys, what, dc);
+        run_t7<4>(amap, H, ys, what, dc);
+        run_t7<6>(amap, H, ys, what, dc);
+        run_t7<8>(amap, H, ys, what, dc);
+        run_t7<12>(amap, H, ys, what, dc);
+      }
+      cudaFree(dx);
+    }
+    cudaFree(dc);
+  }
+  // ------------------------------ T8
+  if (getenv("PROBE_ALL")) {
+    long long* dc;
+    CK(cudaMalloc(&dc, 16));
+    CK(cudaFuncSetAttribute(t8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int n : {12, 24, 48, 96, 192, 384, 768}) {
+      for (int rep = 0; rep < 2; ++rep) {
+        t8_kernel<<<1, 128, 200 * 1024>>>(n, dc);
+        CK(cudaDeviceSynchronize());
+      }
+      long long h[2];
+      CK(cudaMemcpy(h, dc, 16, cudaMemcpyDeviceToHost));
+      printf("T8 %4d MMAs N96: issue returned after %6lld cyc (%.1f/mma), all complete after %6lld cyc (%.1f/mma)\n", n, h[0],
+             (double)h[0] / n, h[1], (double)h[1] / n);
+    }
+    cudaFree(dc);
+  }
+  // ------------------------------ T9
+  {
+    const int rows = 256;
+    uint8_t* buf;
+    const size_t bytes = (size_t)148 * 8 * rows * 32 * 384;
+    CK(cudaMalloc(&buf, bytes));
+    long long* dc;
+    CK(cudaMalloc(&dc, 148 * 8));
+    const char* names[] = {"lane=pixel 2x32B (now, conv1-4)", "lane pair=pixel 64B", "contiguous 1KB (reference)",
+                           "lane=pixel 4x32B (now, conv5)", "4 lanes=pixel full 128B line"};
+    for (int cfg = 0; cfg < 4; ++cfg) {
+      const int wrap = cfg == 0 ? rows : 2;
+      const int nwarps = cfg <= 1 ? 8 : (cfg == 2 ? 2 : 1);
+      printf("T9 footprint %s, %d storing warps per SM\n", cfg == 0 ? "3.7 GB (DRAM)" : "29 MB (L2)", nwarps);
+      for (int mode = 0; mode < 5; ++mode) {
+        for (int rep = 0; rep < 2; ++rep) {
+          t9_kernel<<<148, 256>>>(buf, rows, mode, dc, wrap, nwarps);
+          CK(cudaDeviceSynchronize());
+        }
+        std::vector<long long> hc(148);
+        CK(cudaMemcpy(hc.data(), dc, 148 * 8, cudaMemcpyDeviceToHost));
+        long long mx = 0;
+        for (auto v : hc) mx = v > mx ? v : mx;
+        const double bytes_row = (mode >= 3 ? 4096.0 : 2048.0);
+        printf("T9   %-34s : %.0f cyc per warp-row -> %.1f B/cyc/SM\n", names[mode], (double)mx / rows,
+               bytes_row * nwarps * rows / mx);
+      }
+    }
+    cudaFree(buf);
     cudaFree(dc);
   }
   printf("probe done\n");
