@@ -1,7 +1,7 @@
 """CPU emulation of the GPU path's rounding points (test infrastructure; torch CPU fp32).
 
 Mirrors csrc/b200sr.cu::run_region for the RRDBNet: 16-bit activations/weights at exactly the places
-the engine stores them, fp32 accumulation, fp32 residual trunk.  Used to predict the parity gate
+the engine stores them, fp32 accumulation, residual stream stored as a bf16 hi + e5m2 lo pair.  Used to predict the parity gate
 without a GPU and to tell rounding effects from bugs when a GPU result differs from the oracle.
 """
 from __future__ import annotations
@@ -19,18 +19,19 @@ def _q(t: torch.Tensor, dtype) -> torch.Tensor:
 
 def emulate_rrdb(sd: Dict[str, torch.Tensor], img_bgr_u8: np.ndarray, scale: int = 4, num_block: int = 23,
                  act_dtype=torch.bfloat16, w_dtype=torch.bfloat16, trunk_copy_dtype="same", tail_dtype="same",
-                 first_dtype="same", tail_w_dtype="same", trunk_mode="f32") -> np.ndarray:
+                 first_dtype="same", tail_w_dtype="same", trunk_mode="hilo") -> np.ndarray:
     trunk_copy_dtype = act_dtype if trunk_copy_dtype == "same" else trunk_copy_dtype
     tail_dtype = act_dtype if tail_dtype == "same" else tail_dtype
     first_dtype = act_dtype if first_dtype == "same" else first_dtype
     tail_w_dtype = w_dtype if tail_w_dtype == "same" else tail_w_dtype
 
     def tq(v):
-        """Residual-stream storage: fp32, a bf16 hi + bf16 lo pair (hi is the conv-input copy), or bf16 alone."""
+        """Residual-stream storage: "hilo" = bf16 hi (the conv-input copy) + e5m2 lo (the engine, conv3x3_tc.cuh
+        TrunkLo), "f32", or "bf16" alone."""
         if trunk_mode == "f32":
             return v
         hi = _q(v, torch.bfloat16)
-        return hi if trunk_mode == "bf16" else hi + _q(v - hi, torch.bfloat16)
+        return hi if trunk_mode == "bf16" else hi + (v - hi).to(torch.float8_e5m2).float()
 
     def conv(x, name, wq=True, wd="trunk"):
         w = sd[name + ".weight"].float()

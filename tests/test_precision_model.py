@@ -1,7 +1,7 @@
 """CPU emulation of the GPU path's rounding points (tests/emulate.py) against the fp32 oracle.
 
-This is the design check behind the 16-bit format choice: bf16 RRDB trunk with an fp32 residual
-stream + fp16 HR tail passes the BASELINE gate (>= 99.9 % of pixels within 1 LSB, PSNR >= 45 dB); an all-bf16 tail
+This is the design check behind the storage-format choice: bf16 RRDB trunk whose residual stream is
+kept as a bf16 hi + e5m2 lo pair (as good as fp32; bf16 alone fails) + fp16 HR tail passes the BASELINE gate (>= 99.9 % of pixels within 1 LSB, PSNR >= 45 dB); an all-bf16 tail
 does not on high-frequency input; SRVGG (no fp32 trunk) needs fp16 throughout.
 """
 import torch
@@ -27,6 +27,19 @@ def test_rrdb_mixed_formats_pass_gate():
     # the all-bf16 variant is measurably worse (this is why the tail is fp16)
     rep_bf16 = oracle.parity_report(ref, emulate_rrdb(sd, img))
     assert rep_bf16["psnr_db"] < rep["psnr_db"] - 2.0, (rep_bf16, rep)
+
+
+def test_rrdb_residual_pair_matches_fp32_stream():
+    """hi + lo (bf16 + e5m2) residual storage costs nothing measurable against an fp32 stream; bf16 alone fails."""
+    name = "RealESRGAN_x4plus"
+    sd = make_synthetic_state_dict(name, 0)
+    img = oracle.synthetic_frame(40, 72, seed=3, kind="noise")
+    ref = _ref(name, sd, img)
+    rep = {m: oracle.parity_report(ref, emulate_rrdb(sd, img, tail_dtype=torch.float16, tail_w_dtype=torch.float16,
+                                                     trunk_mode=m)) for m in ("hilo", "f32", "bf16")}
+    assert rep["hilo"]["frac_within_1lsb"] >= oracle.GATE_FRAC_WITHIN_1LSB, rep
+    assert rep["hilo"]["psnr_db"] >= rep["f32"]["psnr_db"] - 0.3, rep
+    assert rep["bf16"]["frac_within_1lsb"] < oracle.GATE_FRAC_WITHIN_1LSB, rep
 
 
 def test_srvgg_fp16_passes_gate_and_beats_bf16():

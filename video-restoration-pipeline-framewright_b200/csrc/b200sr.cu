@@ -312,10 +312,11 @@ size_t region_ws_bytes(const b200sr_engine* e, int N, int H, int W) {
   auto add = [&](size_t b) { total += align_up(b, 1024); };
   if (e->desc.arch == B200SR_ARCH_RRDB) {
     add(px * 192 * 2);
-    add(px * 192 * 2);            // dense ping-pong
-    add(pxt * 64 * 4);
-    add(pxt * 64 * 4);
-    add(pxt * 64 * 4);            // xa, xb, f0 (tile-interleaved layout)
+    add(px * 192 * 2);
+    add(px * 192 * 2);            // dense-block tensors P, Q, R (one per RDB of an RRDB)
+    add(pxt * 64);
+    add(pxt * 64);                // residual-stream lo bytes A, B
+    add(pxt * 64 * 4);            // f0 (tile-interleaved fp32)
     add(px * 64 * 2);             // conv_body out
     add(px * 4 * 64 * 2);
     add(px * 4 * 64 * 2);         // 2x: upsampled, conv_up1 out
@@ -417,8 +418,15 @@ int ensure_rdb_table(b200sr_engine* e, int N, int H, int W, cudaStream_t st) {
 }
 
 // One RDB (layers li .. li+4) as one persistent kernel.
-int launch_rdb_fused(b200sr_engine* e, int li, bool rrdb_end, __nv_bfloat16* Dcur, __nv_bfloat16* Dnext, float* xa,
-                     float* xb, int N, int H, int W, cudaStream_t st) {
+struct TrunkIO {   // residual-stream operands of one RDB's conv5 (TrunkLo, conv3x3_tc.cuh)
+  const uint8_t* lo_in;
+  uint8_t* lo_out;
+  const __nv_bfloat16* xb_hi;
+  const uint8_t* xb_lo;
+};
+
+int launch_rdb_fused(b200sr_engine* e, int li, bool rrdb_end, __nv_bfloat16* Dcur, __nv_bfloat16* Dnext,
+                     const TrunkIO& tio, int N, int H, int W, cudaStream_t st) {
   int rc = ensure_rdb_table(e, N, H, W, st);
   if (rc) return rc;
   CUtensorMap amap;
@@ -444,8 +452,11 @@ int launch_rdb_fused(b200sr_engine* e, int li, bool rrdb_end, __nv_bfloat16* Dcu
       c.out = Dnext;
       c.out_pitch = 192;
       c.out_choff = 0;
-      c.xa = xa;
-      c.xb = xb;
+      c.hi_in = Dcur;
+      c.lo_in = tio.lo_in;
+      c.lo_out = tio.lo_out;
+      c.xb_hi = tio.xb_hi;
+      c.xb_lo = tio.xb_lo;
     }
     flops += 2.0 * 9.0 * l.cin * l.cout * static_cast<double>(N) * H * W;
   }
@@ -480,7 +491,7 @@ int launch_rdb_fused(b200sr_engine* e, int li, bool rrdb_end, __nv_bfloat16* Dcu
 }
 
 int run_first(b200sr_engine* e, const Region& R, int s, int H, int W, __nv_bfloat16* out, int out_pitch, int out_fp16,
-              float* xa, float* xb, float* f0, float* inrgb, const float* prelu, cudaStream_t st) {
+              uint8_t* lo, float* f0, float* inrgb, const float* prelu, cudaStream_t st) {
   const Layer& l = e->layers[0];
   FirstArgs a{};
   a.src = R.src;
@@ -501,8 +512,7 @@ int run_first(b200sr_engine* e, const Region& R, int s, int H, int W, __nv_bfloa
   a.out = out;
   a.out_pitch = out_pitch;
   a.out_fp16 = out_fp16;
-  a.xa = xa;
-  a.xb = xb;
+  a.lo = lo;
   a.f0 = f0;
   a.inrgb = inrgb;
   dim3 grid((W + 127) / 128, H, R.n);
@@ -609,12 +619,14 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
   base.dst_x0 = R.dst_x0;
 
   if (d.arch == B200SR_ARCH_RRDB) {
-    __nv_bfloat16* D[2];
-    D[0] = reinterpret_cast<__nv_bfloat16*>(take(px * 192 * 2));
-    D[1] = reinterpret_cast<__nv_bfloat16*>(take(px * 192 * 2));
+    // Dense-block tensors: RDB r of every RRDB reads D[r] (x.hi in channels 0..63, its own conv1-4 outputs behind)
+    // and writes the next x.hi into D[(r + 1) % 3]; D[0] therefore still holds the RRDB input x0.hi when the third
+    // RDB needs it, and is overwritten pixel by pixel by the thread that has just read it.
+    __nv_bfloat16* D[3];
+    for (int i = 0; i < 3; ++i) D[i] = reinterpret_cast<__nv_bfloat16*>(take(px * 192 * 2));
     const size_t pxt = static_cast<size_t>(N) * H * ((W + 127) / 128) * 128;
-    float* xa = reinterpret_cast<float*>(take(pxt * 64 * 4));
-    float* xb = reinterpret_cast<float*>(take(pxt * 64 * 4));
+    uint8_t* loA = take(pxt * 64);   // x.lo inside an RRDB
+    uint8_t* loB = take(pxt * 64);   // x0.lo (RRDB input), rewritten in place at the RRDB end
     float* f0 = reinterpret_cast<float*>(take(pxt * 64 * 4));
     __nv_bfloat16* U0 = reinterpret_cast<__nv_bfloat16*>(take(px * 64 * 2));
     __nv_bfloat16* U1 = reinterpret_cast<__nv_bfloat16*>(take(px * 4 * 64 * 2));
@@ -622,36 +634,46 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
     __nv_bfloat16* U3 = reinterpret_cast<__nv_bfloat16*>(take(px * 16 * 64 * 2));
     __nv_bfloat16* U4 = reinterpret_cast<__nv_bfloat16*>(take(px * 16 * 64 * 2));
 
-    rc = run_first(e, R, s, H, W, D[0], 192, 0, xa, xb, f0, nullptr, nullptr, st);
+    rc = run_first(e, R, s, H, W, D[0], 192, 0, loB, f0, nullptr, nullptr, st);
     if (rc) return rc;
-    int li = 1, cur_d = 0;
+    int li = 1;
+    const int cur_d = 0;   // the trunk ends where it started
     for (int b = 0; b < d.num_block; ++b)
       for (int r = 0; r < 3; ++r) {
+        __nv_bfloat16* Din = D[r];
+        __nv_bfloat16* Dout = D[(r + 1) % 3];
+        TrunkIO tio;
+        tio.lo_in = r == 0 ? loB : loA;
+        tio.lo_out = r == 2 ? loB : loA;
+        tio.xb_hi = D[0];
+        tio.xb_lo = loB;
         if (e->opt_fused_rdb) {
-          rc = launch_rdb_fused(e, li, r == 2, D[cur_d], D[cur_d ^ 1], xa, xb, N, H, W, st);
+          rc = launch_rdb_fused(e, li, r == 2, Din, Dout, tio, N, H, W, st);
           if (rc) return rc;
           li += 5;
         } else {
-          ConvIO io{D[cur_d], 192, N, H, W};
+          ConvIO io{Din, 192, N, H, W};
           for (int k = 0; k < 4; ++k) {
             ConvArgs a = base;
             a.slope = 0.2f;
-            a.out = D[cur_d];
+            a.out = Din;
             a.out_pitch = 192;
             a.out_choff = 64 + 32 * k;
             rc = launch_conv(e, e->layers[li++], EPI_ACT_BF16, io, a, st);
             if (rc) return rc;
           }
           ConvArgs a = base;
-          a.out = D[cur_d ^ 1];
+          a.out = Dout;
           a.out_pitch = 192;
           a.out_choff = 0;
-          a.xa = xa;
-          a.xb = xb;
+          a.hi_in = Din;
+          a.lo_in = tio.lo_in;
+          a.lo_out = tio.lo_out;
+          a.xb_hi = tio.xb_hi;
+          a.xb_lo = tio.xb_lo;
           rc = launch_conv(e, e->layers[li++], r == 2 ? EPI_RDB5_RRDB : EPI_RDB5, io, a, st);
           if (rc) return rc;
         }
-        cur_d ^= 1;
       }
     {  // conv_body: feat + conv_body(body(feat))
       ConvIO io{D[cur_d], 192, N, H, W};
@@ -707,7 +729,7 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
     S[0] = reinterpret_cast<__nv_bfloat16*>(take(px * 64 * 2));
     S[1] = reinterpret_cast<__nv_bfloat16*>(take(px * 64 * 2));
     float* inrgb = reinterpret_cast<float*>(take(px * 4 * 4));
-    rc = run_first(e, R, 1, H, W, S[0], 64, 1, nullptr, nullptr, nullptr, inrgb, e->prelu_dev[0], st);
+    rc = run_first(e, R, 1, H, W, S[0], 64, 1, nullptr, nullptr, inrgb, e->prelu_dev[0], st);
     if (rc) return rc;
     int cur_s = 0;
     for (int i = 0; i < d.num_block; ++i) {

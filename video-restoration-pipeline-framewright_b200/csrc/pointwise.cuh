@@ -23,9 +23,8 @@ struct FirstArgs {
   __nv_bfloat16* out;   // 16-bit NHWC (bf16, or fp16 when out_fp16)
   int out_pitch;
   int out_fp16;
-  float* xa;            // optional fp32 copies of the result ([N][H][W][64])
-  float* xb;
-  float* f0;
+  uint8_t* lo;          // optional: e5m2 residual of the 16-bit result (TrunkLo layout, conv3x3_tc.cuh)
+  float* f0;            // optional: fp32 copy of the result (tile-interleaved layout)
   float* inrgb;         // optional normalised network input [N][H][W][4] (RGB0), s == 1 only
 };
 
@@ -95,19 +94,18 @@ __global__ void __launch_bounds__(128) first_conv_kernel(const FirstArgs a) {
     for (int c = 0; c < 64; ++c) acc[c] = acc[c] > 0.f ? acc[c] : acc[c] * s_p[c];
   }
   const size_t pix = (static_cast<size_t>(n) * a.H + y) * a.W + x;
-  store_bf16_row<64>(a.out + pix * a.out_pitch, acc, a.out_fp16);
-  float* f32dst[3] = {a.xa, a.xb, a.f0};
+  if (a.lo)
+    store_trunk_pair(a.out + pix * a.out_pitch, a.lo + lo_off(n, y, x, a.H, a.W), acc);
+  else
+    store_bf16_row<64>(a.out + pix * a.out_pitch, acc, a.out_fp16);
+  if (a.f0) {
+    float* d = a.f0 + trunk_off(n, y, x, a.H, a.W);   // tile-interleaved fp32 layout
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    if (f32dst[k]) {
-      float* d = f32dst[k] + trunk_off(n, y, x, a.H, a.W);   // tile-interleaved fp32 trunk layout
+    for (int g = 0; g < 8; ++g) {
+      uint32_t o[8];
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint32_t o[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(acc[g * 8 + i]);
-        st_global_256(d + g * TRUNK_GSTRIDE, o);
-      }
+      for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(acc[g * 8 + i]);
+      st_global_256(d + g * TRUNK_GSTRIDE, o);
     }
   }
   if (a.inrgb) *reinterpret_cast<float4*>(a.inrgb + pix * 4) = make_float4(centre[0], centre[1], centre[2], 0.f);

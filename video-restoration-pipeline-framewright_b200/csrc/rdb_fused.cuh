@@ -73,40 +73,6 @@ __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
 // generic -> async proxy ordering for GLOBAL memory only (the unrestricted form also covers shared memory)
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
-// conv5 tail of one pixel with the fp32 trunk row `xr` already in registers (loaded while the MMAs were still
-// running): x <- (acc + b) * 0.2 + x ; optionally x <- x * 0.2 + x0 and x0 <- x (RRDB end); + bf16 copy.
-template <bool RRDB>
-__device__ __forceinline__ void rdb5_pixel(const ConvArgs& a, const float* s_bias, float (&acc)[64],
-                                           const uint32_t (&xr)[8][8], int n, int y, int x) {
-  const size_t pix = (static_cast<size_t>(n) * a.H + y) * a.W + x;
-  const size_t toff = trunk_off(n, y, x, a.H, a.W);
-  float* xa = a.xa + toff;
-  float* xb = a.xb + toff;
-#pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    uint32_t r0[4][8];
-    if constexpr (RRDB) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) ld_global_256_nv(xb + (hh * 4 + g) * TRUNK_GSTRIDE, r0[g]);
-    }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint32_t o[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = hh * 32 + g * 8 + i;
-        float v = (acc[c] + s_bias[c]) * 0.2f + __uint_as_float(xr[hh * 4 + g][i]);
-        if constexpr (RRDB) v = v * 0.2f + __uint_as_float(r0[g][i]);
-        acc[c] = v;
-        o[i] = __float_as_uint(v);
-      }
-      if constexpr (RRDB) st_global_256(xb + (hh * 4 + g) * TRUNK_GSTRIDE, o);
-      st_global_256(xa + (hh * 4 + g) * TRUNK_GSTRIDE, o);
-    }
-  }
-  store_bf16_row<64>(a.out + pix * a.out_pitch + a.out_choff, acc, 0);
-}
-
 // Dev instrumentation (per-role wait / issue cycle counters, tools/rdb_stats.py): compiled in only with
 // -DB200SR_RDB_STATS.  It costs registers and local-memory traffic, so product builds leave it out.
 #ifdef B200SR_RDB_STATS
@@ -527,25 +493,28 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
       const int n = item.n;
       const int x = item.tx * 128 + m;
       if (item.k == 4) {
-        // pull the fp32 residual rows of this item towards L2 while the MMAs run (8 groups x 1 KB per warp-row)
+        // pull the residual (lo) rows of this item towards L2 while the MMAs run (2 groups x 1 KB per warp-row);
+        // the hi rows arrive with the chunk-0 TMA loads
         for (int Y = eg; Y < item.rows; Y += 2) {
-          const size_t wbase = trunk_off(n, item.y0 + Y, item.tx * 128 + q * 32, L.H, L.W) + (lane & 7) * 32;
-#pragma unroll
-          for (int t2 = 0; t2 < 2; ++t2) {
-            const size_t o = wbase + static_cast<size_t>(t2 * 4 + (lane >> 3)) * TRUNK_GSTRIDE;
-            prefetch_l2(L.xa + o);
-            if (args.rrdb_end) prefetch_l2(L.xb + o);
+          const size_t o = lo_off(n, item.y0 + Y, item.tx * 128 + q * 32, L.H, L.W) + (lane & 7) * 128 +
+                           static_cast<size_t>((lane >> 3) & 1) * LO_GSTRIDE;
+          if (lane < 16) {
+            prefetch_l2(L.lo_in + o);
+            if (args.rrdb_end) prefetch_l2(L.xb_lo + o);
           }
         }
         for (int Y = 0; Y < item.rows; ++Y) {
           const int sl = 2 * Y;
           if ((Y & 1) == eg) {
-            // fetch this pixel's fp32 trunk row now, while the MMAs of the row are still in flight
-            uint32_t xr[8][8];
+            // fetch this pixel's x pair now, while the MMAs of the row are still in flight
+            uint32_t xh[4][8], xl[2][8];
             if (x < L.W) {
-              const float* xa = L.xa + trunk_off(n, item.y0 + Y, x, L.H, L.W);
+              const __nv_bfloat16* hp = L.hi_in + ((static_cast<size_t>(n) * L.H + item.y0 + Y) * L.W + x) * L.out_pitch;
+              const uint8_t* lp = L.lo_in + lo_off(n, item.y0 + Y, x, L.H, L.W);
 #pragma unroll
-              for (int g = 0; g < 8; ++g) ld_global_256(xa + g * TRUNK_GSTRIDE, xr[g]);
+              for (int g = 0; g < 4; ++g) ld_global_256(hp + g * 16, xh[g]);
+#pragma unroll
+              for (int g = 0; g < 2; ++g) ld_global_256(lp + g * LO_GSTRIDE, xl[g]);
             }
             RDB_TIMED(0, mbar_wait(&bar_rfull[sl], (rfull_par >> sl) & 1u));
             if (q == 2 && lane == 0) RDB_STAMP2(it, Y, 1);
@@ -561,9 +530,9 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             RDB_TIMED(2, {
               if (x < L.W && !(B200SR_ABL_NOEPI & 2)) {
                 if (args.rrdb_end)
-                  rdb5_pixel<true>(L, s_bias[4], acc, xr, n, item.y0 + Y, x);
+                  trunk_pixel<true>(L, s_bias[4], acc, xh, xl, n, item.y0 + Y, x);
                 else
-                  rdb5_pixel<false>(L, s_bias[4], acc, xr, n, item.y0 + Y, x);
+                  trunk_pixel<false>(L, s_bias[4], acc, xh, xl, n, item.y0 + Y, x);
               }
             });
             RDB_COUNT(3, 1);
