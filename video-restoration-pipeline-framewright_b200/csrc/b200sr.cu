@@ -262,15 +262,18 @@ struct ConvIO {
   const void* in;   // bf16 NHWC input tensor
   int in_pitch;     // channels per pixel
   int N, H, W;
+  int planes = 0;   // > 0: chunk-planar input (ConvArgs::in_planes): `planes` tensors [N][H][W][64] back to back
 };
 
 int launch_conv(b200sr_engine* e, const Layer& l, int epi, const ConvIO& io, ConvArgs a, cudaStream_t st) {
   CUtensorMap amap;
-  if (!tmap_encode_act(&amap, io.in, io.N, io.H, io.W, io.in_pitch, 64, ConvCfg<64>::A_ROWS, 128))
+  if (!tmap_encode_act(&amap, io.in, io.planes ? io.planes * io.N : io.N, io.H, io.W, io.in_pitch, 64, ConvCfg<64>::A_ROWS,
+                       128))
     return fail(e, B200SR_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   a.N = io.N;
   a.H = io.H;
   a.W = io.W;
+  a.in_planes = io.planes;
   a.nchunks = (l.cin + 63) / 64;
   a.last_ksteps = (l.cin % 64 == 32) ? 2 : 4;
   a.TH = choose_th(e, l.coutp, io.N, io.H, io.W);
@@ -430,7 +433,8 @@ int launch_rdb_fused(b200sr_engine* e, int li, bool rrdb_end, __nv_bfloat16* Dcu
   int rc = ensure_rdb_table(e, N, H, W, st);
   if (rc) return rc;
   CUtensorMap amap;
-  if (!tmap_encode_act(&amap, Dcur, N, H, W, 192, 64, 130, 128)) return fail(e, B200SR_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  if (!tmap_encode_act(&amap, Dcur, 3 * N, H, W, 64, 64, 130, 128)) return fail(e, B200SR_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  const size_t plane = static_cast<size_t>(N) * H * W * 64;   // elements per chunk plane
   RdbArgs a{};
   double flops = 0;
   for (int k = 0; k < 5; ++k) {
@@ -444,13 +448,14 @@ int launch_rdb_fused(b200sr_engine* e, int li, bool rrdb_end, __nv_bfloat16* Dcu
     c.wpack = l.d_wpack;
     c.bias = l.d_bias;
     c.slope = 0.2f;
+    c.in_planes = 3;
     if (k < 4) {
-      c.out = Dcur;
-      c.out_pitch = 192;
-      c.out_choff = 64 + 32 * k;
+      c.out = Dcur + (1 + k / 2) * plane;
+      c.out_pitch = 64;
+      c.out_choff = 32 * (k & 1);
     } else {
       c.out = Dnext;
-      c.out_pitch = 192;
+      c.out_pitch = 64;
       c.out_choff = 0;
       c.hi_in = Dcur;
       c.lo_in = tio.lo_in;
@@ -619,9 +624,12 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
   base.dst_x0 = R.dst_x0;
 
   if (d.arch == B200SR_ARCH_RRDB) {
-    // Dense-block tensors: RDB r of every RRDB reads D[r] (x.hi in channels 0..63, its own conv1-4 outputs behind)
-    // and writes the next x.hi into D[(r + 1) % 3]; D[0] therefore still holds the RRDB input x0.hi when the third
-    // RDB needs it, and is overwritten pixel by pixel by the thread that has just read it.
+    // Dense-block tensors, chunk-planar: plane 0 = x.hi (64 ch), plane 1 = conv1|conv2 outputs, plane 2 =
+    // conv3|conv4 outputs, each [N][H][W][64] (128 B per pixel, pixels contiguous: a TMA row box is one contiguous
+    // 16.6 KB read and DRAM pages are used whole; with one 384 B-pitch NHWC tensor every box row was a separate
+    // 128 B access).  RDB r of every RRDB reads D[r] and writes the next x.hi into plane 0 of D[(r + 1) % 3]; D[0]
+    // therefore still holds the RRDB input x0.hi when the third RDB needs it, and is overwritten pixel by pixel
+    // by the thread that has just read it.
     __nv_bfloat16* D[3];
     for (int i = 0; i < 3; ++i) D[i] = reinterpret_cast<__nv_bfloat16*>(take(px * 192 * 2));
     const size_t pxt = static_cast<size_t>(N) * H * ((W + 127) / 128) * 128;
@@ -634,7 +642,8 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
     __nv_bfloat16* U3 = reinterpret_cast<__nv_bfloat16*>(take(px * 16 * 64 * 2));
     __nv_bfloat16* U4 = reinterpret_cast<__nv_bfloat16*>(take(px * 16 * 64 * 2));
 
-    rc = run_first(e, R, s, H, W, D[0], 192, 0, loB, f0, nullptr, nullptr, st);
+    const size_t plane = px * 64;
+    rc = run_first(e, R, s, H, W, D[0], 64, 0, loB, f0, nullptr, nullptr, st);
     if (rc) return rc;
     int li = 1;
     const int cur_d = 0;   // the trunk ends where it started
@@ -652,19 +661,19 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
           if (rc) return rc;
           li += 5;
         } else {
-          ConvIO io{Din, 192, N, H, W};
+          ConvIO io{Din, 64, N, H, W, 3};
           for (int k = 0; k < 4; ++k) {
             ConvArgs a = base;
             a.slope = 0.2f;
-            a.out = Din;
-            a.out_pitch = 192;
-            a.out_choff = 64 + 32 * k;
+            a.out = Din + (1 + k / 2) * plane;
+            a.out_pitch = 64;
+            a.out_choff = 32 * (k & 1);
             rc = launch_conv(e, e->layers[li++], EPI_ACT_BF16, io, a, st);
             if (rc) return rc;
           }
           ConvArgs a = base;
           a.out = Dout;
-          a.out_pitch = 192;
+          a.out_pitch = 64;
           a.out_choff = 0;
           a.hi_in = Din;
           a.lo_in = tio.lo_in;
@@ -676,7 +685,7 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
         }
       }
     {  // conv_body: feat + conv_body(body(feat))
-      ConvIO io{D[cur_d], 192, N, H, W};
+      ConvIO io{D[cur_d], 64, N, H, W};
       ConvArgs a = base;
       a.out = U0;
       a.out_pitch = 64;

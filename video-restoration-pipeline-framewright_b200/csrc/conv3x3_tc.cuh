@@ -55,6 +55,8 @@ struct ConvArgs {
   const float* bias;      // COUT floats
   const float* prelu;     // COUT floats (EPI_PRELU_BF16)
   float slope;            // leaky slope (EPI_ACT_BF16)
+  int in_planes;          // 0: input chunk c = channels [64c, 64c+64) of one NHWC tensor.  P > 0: chunk-planar
+                          // input, chunk c is its own [N][H][W][64] tensor and image n of it is TMA image c*N + n
   int in_fp16;            // A (activations) and B (weights) are fp16 instead of bf16
   int out_fp16;           // 16-bit output tensor is fp16 instead of bf16
   __nv_bfloat16* out;     // 16-bit NHWC destination (bf16 or fp16 per out_fp16)
@@ -102,7 +104,13 @@ struct ConvCfg {
   static constexpr int NTHREADS = 32 * (2 + NEPI_WARPS);        // warp 0 TMA, warp 1 MMA, rest epilogue
 };
 
+#ifdef B200SR_ABL_STORE_SCRATCH
+__device__ uint8_t g_abl_scratch[8 << 20];
+#endif
 __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
+#ifdef B200SR_ABL_STORE_SCRATCH   // timing ablation (tools only): same store instructions, 8 MB L2-resident target
+  if (B200SR_ABL_STORE_SCRATCH != 2) p = g_abl_scratch + (reinterpret_cast<uintptr_t>(p) & ((8u << 20) - 32));
+#endif
 #ifdef B200SR_ABL_NOSTORE   // timing ablation (tools only): keep the math alive, skip the store
   if (reinterpret_cast<uintptr_t>(p) != 1) return;
 #endif
@@ -115,6 +123,32 @@ __device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&v)[8]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "l"(p)
                : "memory");
+}
+// Evict-first variants for data that is not touched again during the launch (streams through L2 without pushing
+// out the rows other CTAs are about to read).
+__device__ __forceinline__ void st_global_256_ef(void* p, const uint32_t (&v)[8]) {
+#if defined(B200SR_ABL_STORE_SCRATCH)
+  if (B200SR_ABL_STORE_SCRATCH != 3) p = g_abl_scratch + (reinterpret_cast<uintptr_t>(p) & ((8u << 20) - 32));
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+#elif defined(B200SR_ABL_NOSTORE) || defined(B200SR_ABL_NOHINT)
+  st_global_256(p, v);
+#else
+  asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+#endif
+}
+__device__ __forceinline__ void ld_global_256_ef(const void* p, uint32_t (&v)[8]) {
+#if defined(B200SR_ABL_NOHINT)
+  ld_global_256(p, v);
+#else
+  asm volatile("ld.global.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p)
+               : "memory");
+#endif
 }
 // Non-volatile variant: the compiler may hoist and batch these (used for read-only / read-before-write data).
 __device__ __forceinline__ void ld_global_256_nv(const void* p, uint32_t (&v)[8]) {
@@ -242,7 +276,7 @@ __device__ __forceinline__ void store_trunk_pair(__nv_bfloat16* hi_dst, uint8_t*
       r[c] = v[c] - bf16lo_f32(p[i]);
       r[c + 1] = v[c + 1] - bf16hi_f32(p[i]);
     }
-    st_global_256(hi_dst + g * 16, p);
+    st_global_256_ef(hi_dst + g * 16, p);
   }
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
@@ -252,7 +286,7 @@ __device__ __forceinline__ void store_trunk_pair(__nv_bfloat16* hi_dst, uint8_t*
       const int c = g * 32 + 4 * i;
       p[i] = f32x4_e5m2(r[c], r[c + 1], r[c + 2], r[c + 3]);
     }
-    st_global_256(lo_dst + g * LO_GSTRIDE, p);
+    st_global_256_ef(lo_dst + g * LO_GSTRIDE, p);
   }
 }
 
@@ -269,9 +303,9 @@ __device__ __forceinline__ void trunk_pixel(const ConvArgs& a, const float* s_bi
   if constexpr (RRDB) {
     const __nv_bfloat16* xh = a.xb_hi + pix * a.out_pitch;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) ld_global_256(xh + g * 16, h0[g]);
+    for (int g = 0; g < 4; ++g) ld_global_256_ef(xh + g * 16, h0[g]);
 #pragma unroll
-    for (int g = 0; g < 2; ++g) ld_global_256(a.xb_lo + loff + g * LO_GSTRIDE, l0[g]);
+    for (int g = 0; g < 2; ++g) ld_global_256_ef(a.xb_lo + loff + g * LO_GSTRIDE, l0[g]);
   }
 #pragma unroll
   for (int g = 0; g < 2; ++g)
@@ -321,9 +355,9 @@ __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* s
     const __nv_bfloat16* xh = a.hi_in + pix * a.out_pitch;
     const size_t loff = lo_off(n, y, x, a.H, a.W);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) ld_global_256(xh + g * 16, hi[g]);
+    for (int g = 0; g < 4; ++g) ld_global_256_ef(xh + g * 16, hi[g]);
 #pragma unroll
-    for (int g = 0; g < 2; ++g) ld_global_256(a.lo_in + loff + g * LO_GSTRIDE, lo[g]);
+    for (int g = 0; g < 2; ++g) ld_global_256_ef(a.lo_in + loff + g * LO_GSTRIDE, lo[g]);
     trunk_pixel<EPI == EPI_RDB5_RRDB>(a, s_bias, acc, hi, lo, n, y, x);
   } else if constexpr (EPI == EPI_ADD_F32) {
     const float* f = a.fadd + trunk_off(n, y, x, a.H, a.W);
@@ -450,7 +484,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
           mbar_wait(&bar_empty[stage], phase ^ 1);
           if (elect_one_sync()) {
             mbar_arrive_expect_tx(&bar_full[stage], Cfg::A_BOX_BYTES);
-            tma_load_4d(&amap, &bar_full[stage], sA + stage * Cfg::A_STAGE_BYTES, c * 64, x0, y0 + y, n);
+            if (args.in_planes)
+              tma_load_4d(&amap, &bar_full[stage], sA + stage * Cfg::A_STAGE_BYTES, 0, x0, y0 + y, c * args.N + n);
+            else
+              tma_load_4d(&amap, &bar_full[stage], sA + stage * Cfg::A_STAGE_BYTES, c * 64, x0, y0 + y, n);
           }
           __syncwarp();
           if (++stage == Cfg::NSTAGES) {

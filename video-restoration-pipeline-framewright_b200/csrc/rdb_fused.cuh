@@ -26,6 +26,9 @@
 #ifndef B200SR_ABL_NOEPI
 #define B200SR_ABL_NOEPI 0
 #endif
+#ifndef B200SR_ABL_NOPREFETCH
+#define B200SR_ABL_NOPREFETCH 1   // measured: no gain (2126 vs 2068 us per launch at 4 x 720p), off
+#endif
 #ifndef B200SR_ABL_NODEP
 #define B200SR_ABL_NODEP 0
 #endif
@@ -189,6 +192,8 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
     // Items are claimed dynamically, in list order (atomic counter): an item never starts before a lower-numbered
     // one, so a producer item that precedes its consumer by >= one "round" of CTAs has already finished.
     int stage = 0, phase = 0, wb = 0, wphase = 0, qi = 0, qphase = 0;
+    const uint64_t pol_first = make_l2_policy_evict_first(), pol_normal = make_l2_policy_evict_normal();
+    const uint64_t pol_last = make_l2_policy_evict_last();
     // (Claiming an item ahead of time was measured to be much worse: a claimed-but-not-started item delays all its
     // consumers.  Items are claimed exactly when the producer warp is ready to start them.)
     while (true) {
@@ -219,6 +224,17 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
       const int cout = item.k < 4 ? 32 : 64;
       const uint32_t wtile = 3u * cout * 128u;
       const int x0 = item.tx * 128 - 1;
+      // conv5 is the last reader of the dense block's rows in this launch: let them leave L2 first
+#ifdef B200SR_ABL_NOHINT
+      const uint64_t pol_item = pol_normal;
+#else
+      const uint64_t pol_item = item.k == 4 ? pol_first : pol_normal;
+#endif
+#if !B200SR_ABL_NOPREFETCH
+      // Chunk 0 is x.hi, written by the PREVIOUS launch and (for its first reader) still in DRAM: start all of the
+      // item's chunk-0 rows towards L2 now, one box per lane; the 4-stage ring alone covers only ~4 rows of latency.
+      if (lane < item.rows + 2) tma_prefetch_4d(&amap, 0, x0, item.y0 - 1 + lane, item.n);   // plane 0
+#endif
       for (int c = 0; c < L.nchunks; ++c) {
         RDB_TIMED(2, mbar_wait(&bar_wempty[wb], wphase ^ 1));
         if (elect_one_sync()) {
@@ -259,12 +275,19 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
           });
           RDB_STAMP(it, 2 * c);
         }
+        // x.hi (chunk 0) is read by all five convs, ~5 steps apart, with ~100 MB of other traffic in between: keep
+        // it in L2 (evict_last) until conv5, its last reader, has passed (evict_first)
+#ifdef B200SR_ABL_NOHINT
+        const uint64_t pol = pol_item;
+#else
+        const uint64_t pol = c == 0 ? pol_last : pol_item;   // (conv5's epilogue reads x.hi once more)
+#endif
         for (int y = -1; y <= item.rows; ++y) {
           const int r = item.y0 + y;
           RDB_TIMED(1, mbar_wait(&bar_empty[stage], phase ^ 1));
           if (elect_one_sync()) {
             mbar_arrive_expect_tx(&bar_full[stage], 130 * 128);
-            tma_load_4d(&amap, &bar_full[stage], sA + stage * RDB_A_STAGE_BYTES, c * 64, x0, r, item.n);
+            tma_load_4d_hint(&amap, &bar_full[stage], sA + stage * RDB_A_STAGE_BYTES, 0, x0, r, c * L.N + item.n, pol);
           }
           __syncwarp();
           if (++stage == RDB_NSTAGES) {
@@ -493,14 +516,24 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
       const int n = item.n;
       const int x = item.tx * 128 + m;
       if (item.k == 4) {
-        // pull the residual (lo) rows of this item towards L2 while the MMAs run (2 groups x 1 KB per warp-row);
-        // the hi rows arrive with the chunk-0 TMA loads
+        // pull the residual (lo) rows of this item towards L2 while the MMAs run (2 groups x 1 KB per warp-row); the
+        // x.hi rows arrive with the chunk-0 TMA loads.  At the RRDB end also the RRDB input pair x0 (last touched
+        // three launches ago): one 128 B line of x0.hi per pixel.
         for (int Y = eg; Y < item.rows; Y += 2) {
           const size_t o = lo_off(n, item.y0 + Y, item.tx * 128 + q * 32, L.H, L.W) + (lane & 7) * 128 +
                            static_cast<size_t>((lane >> 3) & 1) * LO_GSTRIDE;
           if (lane < 16) {
             prefetch_l2(L.lo_in + o);
             if (args.rrdb_end) prefetch_l2(L.xb_lo + o);
+          }
+          if (x < L.W) {
+            const size_t po = ((static_cast<size_t>(n) * L.H + item.y0 + Y) * L.W + x) * L.out_pitch;
+#ifdef B200SR_ABL_PREFETCH_DST
+            prefetch_l2(L.out + po);   // == xb_hi at the RRDB end
+            if (lane < 16 && L.lo_out != L.lo_in) prefetch_l2(L.lo_out + o);
+#else
+            if (args.rrdb_end) prefetch_l2(L.xb_hi + po);
+#endif
           }
         }
         for (int Y = 0; Y < item.rows; ++Y) {
@@ -512,9 +545,9 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
               const __nv_bfloat16* hp = L.hi_in + ((static_cast<size_t>(n) * L.H + item.y0 + Y) * L.W + x) * L.out_pitch;
               const uint8_t* lp = L.lo_in + lo_off(n, item.y0 + Y, x, L.H, L.W);
 #pragma unroll
-              for (int g = 0; g < 4; ++g) ld_global_256(hp + g * 16, xh[g]);
+              for (int g = 0; g < 4; ++g) ld_global_256_ef(hp + g * 16, xh[g]);
 #pragma unroll
-              for (int g = 0; g < 2; ++g) ld_global_256(lp + g * LO_GSTRIDE, xl[g]);
+              for (int g = 0; g < 2; ++g) ld_global_256_ef(lp + g * LO_GSTRIDE, xl[g]);
             }
             RDB_TIMED(0, mbar_wait(&bar_rfull[sl], (rfull_par >> sl) & 1u));
             if (q == 2 && lane == 0) RDB_STAMP2(it, Y, 1);
