@@ -424,20 +424,38 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
         // full accumulator rows each: N = 3*cout, no edge cases); the last rows through the general path again.
         burst(-1, 2);
         int y = 1;
+        // Interior pairs.  The tensor pipe queues only ~2 instructions, so whatever the issuing thread does between
+        // the last MMA of one burst and the first of the next is a pipe bubble unless it fits into the ~100-190
+        // cycles those two instructions take.  The barrier waits of the NEXT pair (activation stages, and in the
+        // first chunk the TMEM slots it touches first) are therefore PROBED (non-blocking) by the issuing thread just
+        // before the last two MMAs of the current pair: if everything is already there, the next pair starts without
+        // any wait; if not, it waits as usual.  (Blocking there instead was measured slower: it delays this pair's
+        // commits, i.e. the stage hand-back to the producer and the rows' hand-over to the epilogue.)
+        bool waited = false;   // this pair's barriers were already observed by the issuing thread
         for (; y + 1 <= TH - 2; y += 2) {
           const int s0 = stage, s1 = (stage + 1) & (RDB_NSTAGES - 1);
+          const uint32_t p0 = phase, p1 = s1 < s0 ? (phase ^ 1) : phase;
           if (first_chunk) {   // accumulator rows y+1 and y+2 are touched for the first time
             for (int sl = (y + 1) * spr; sl < (y + 3) * spr; ++sl) {
-              RDB_TIMED(1, mbar_wait(&bar_rempty[sl], (rempty_par >> sl) & 1u));
+              if (!waited) RDB_TIMED(1, mbar_wait(&bar_rempty[sl], (rempty_par >> sl) & 1u));
               rempty_par ^= 1u << sl;
             }
           }
-          RDB_TIMED(2, mbar_wait(&bar_full[s0], phase));
-          RDB_TIMED(2, mbar_wait(&bar_full[s1], s1 < s0 ? (phase ^ 1) : phase));
+          if (!waited) {
+            RDB_TIMED(2, mbar_wait(&bar_full[s0], p0));
+            RDB_TIMED(2, mbar_wait(&bar_full[s1], p1));
+          }
           tc_fence_after();
+          // the next interior pair (if any): its stages / parities / first-touch slots
+          const bool has_next = (y + 3) <= TH - 2;
+          const int nst = (stage + 2) & (RDB_NSTAGES - 1);
+          const uint32_t nph = (stage + 2 >= RDB_NSTAGES) ? (phase ^ 1) : phase;
+          const int n0 = nst, n1 = (nst + 1) & (RDB_NSTAGES - 1);
+          const uint32_t np0 = nph, np1 = n1 < n0 ? (nph ^ 1) : nph;
           const uint32_t dc0 = tmem_base + static_cast<uint32_t>((y - 1) * cout);
           const uint64_t a0 = adesc0 + static_cast<uint64_t>((s0 * RDB_A_STAGE_BYTES) >> 4);
           const uint64_t a1 = adesc0 + static_cast<uint64_t>((s1 * RDB_A_STAGE_BYTES) >> 4);
+          bool next_ready = false;   // (issuing thread) the next pair's barriers were all found complete
           if (elect_one_sync()) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -452,6 +470,13 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
               if (ks == 4) {
 #pragma unroll
                 for (int i = 1; i < 12; ++i) {
+                  if (j == 1 && i == 10 && has_next) {
+                    bool ok = mbar_test_wait(&bar_full[n0], np0) && mbar_test_wait(&bar_full[n1], np1);
+                    if (first_chunk)
+                      for (int sl = (y + 3) * spr; sl < (y + 5) * spr; ++sl)
+                        ok = ok && mbar_test_wait(&bar_rempty[sl], (rempty_par >> sl) & 1u);
+                    next_ready = ok;
+                  }
                   const int dx = i >> 2, k = i & 3;
                   umma_bf16(dc, ad + static_cast<uint64_t>((dx * 128 + k * 32) >> 4),
                             bdesc_w + static_cast<uint64_t>((dx * wtile + k * 32) >> 4), idesc3, 1);
@@ -459,6 +484,13 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
               } else {
 #pragma unroll
                 for (int i = 1; i < 6; ++i) {
+                  if (j == 1 && i == 4 && has_next) {
+                    bool ok = mbar_test_wait(&bar_full[n0], np0) && mbar_test_wait(&bar_full[n1], np1);
+                    if (first_chunk)
+                      for (int sl = (y + 3) * spr; sl < (y + 5) * spr; ++sl)
+                        ok = ok && mbar_test_wait(&bar_rempty[sl], (rempty_par >> sl) & 1u);
+                    next_ready = ok;
+                  }
                   const int dx = i >> 1, k = i & 1;
                   umma_bf16(dc, ad + static_cast<uint64_t>((dx * 128 + k * 32) >> 4),
                             bdesc_w + static_cast<uint64_t>((dx * wtile + k * 32) >> 4), idesc3, 1);
@@ -471,7 +503,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
               }
             }
           }
-          __syncwarp();
+          waited = __any_sync(0xffffffffu, next_ready);
           stage += 2;
           if (stage >= RDB_NSTAGES) {
             stage -= RDB_NSTAGES;
@@ -517,23 +549,14 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
       const int x = item.tx * 128 + m;
       if (item.k == 4) {
         // pull the residual (lo) rows of this item towards L2 while the MMAs run (2 groups x 1 KB per warp-row); the
-        // x.hi rows arrive with the chunk-0 TMA loads.  At the RRDB end also the RRDB input pair x0 (last touched
-        // three launches ago): one 128 B line of x0.hi per pixel.
+        // x.hi rows arrive with the chunk-0 TMA loads.  At the RRDB end also x0.lo of the RRDB input pair (last
+        // touched three launches ago; prefetching x0.hi as well measured ~1 % slower, more early DRAM traffic).
         for (int Y = eg; Y < item.rows; Y += 2) {
           const size_t o = lo_off(n, item.y0 + Y, item.tx * 128 + q * 32, L.H, L.W) + (lane & 7) * 128 +
                            static_cast<size_t>((lane >> 3) & 1) * LO_GSTRIDE;
           if (lane < 16) {
             prefetch_l2(L.lo_in + o);
             if (args.rrdb_end) prefetch_l2(L.xb_lo + o);
-          }
-          if (x < L.W) {
-            const size_t po = ((static_cast<size_t>(n) * L.H + item.y0 + Y) * L.W + x) * L.out_pitch;
-#ifdef B200SR_ABL_PREFETCH_DST
-            prefetch_l2(L.out + po);   // == xb_hi at the RRDB end
-            if (lane < 16 && L.lo_out != L.lo_in) prefetch_l2(L.lo_out + o);
-#else
-            if (args.rrdb_end) prefetch_l2(L.xb_hi + po);
-#endif
           }
         }
         for (int Y = 0; Y < item.rows; ++Y) {
