@@ -81,6 +81,7 @@ struct b200sr_engine {
   bool attrs_set = false;
   // optional per-kernel-class timing (CUDA events around every launch; option "profile")
   int opt_fused_rdb = 1;    // run each RDB as one persistent kernel (L2-resident intermediates)
+  int opt_fold_up = 1;      // conv_up1/up2 read the nearest-2x upsampling through the duplicated-pixel TMA view
   int opt_rdb_stats = 0;    // dev: collect per-CTA cycle counters of the k-th fused launch of a forward pass (1-based)
   int rdb_launch_idx = 0;
   long long* d_rdb_stats = nullptr;
@@ -263,17 +264,20 @@ struct ConvIO {
   int in_pitch;     // channels per pixel
   int N, H, W;
   int planes = 0;   // > 0: chunk-planar input (ConvArgs::in_planes): `planes` tensors [N][H][W][64] back to back
+  int up2 = 0;      // `in` is [N][H/2][W/2][pitch]; the conv reads its nearest-2x upsampling (ConvArgs::in_up2)
 };
 
 int launch_conv(b200sr_engine* e, const Layer& l, int epi, const ConvIO& io, ConvArgs a, cudaStream_t st) {
   CUtensorMap amap;
-  if (!tmap_encode_act(&amap, io.in, io.planes ? io.planes * io.N : io.N, io.H, io.W, io.in_pitch, 64, ConvCfg<64>::A_ROWS,
-                       128))
-    return fail(e, B200SR_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  const bool map_ok = io.up2 ? tmap_encode_act_up2(&amap, io.in, io.N, io.H / 2, io.W / 2, io.in_pitch, 64, 66, 128)
+                             : tmap_encode_act(&amap, io.in, io.planes ? io.planes * io.N : io.N, io.H, io.W, io.in_pitch,
+                                               64, ConvCfg<64>::A_ROWS, 128);
+  if (!map_ok) return fail(e, B200SR_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   a.N = io.N;
   a.H = io.H;
   a.W = io.W;
   a.in_planes = io.planes;
+  a.in_up2 = io.up2;
   a.nchunks = (l.cin + 63) / 64;
   a.last_ksteps = (l.cin % 64 == 32) ? 2 : 4;
   a.TH = choose_th(e, l.coutp, io.N, io.H, io.W);
@@ -694,10 +698,14 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
       rc = launch_conv(e, e->layers[li++], EPI_ADD_F32, io, a, st);
       if (rc) return rc;
     }
-    rc = run_upsample(e, U0, U1, N, H, W, st);
-    if (rc) return rc;
+    // conv_up1/conv_up2 read F.interpolate(x, 2, 'nearest') of their input straight from the low-resolution
+    // tensor through the duplicated-pixel TMA view (option fold_up = 0: materialise it with upsample2x_kernel)
+    if (!e->opt_fold_up) {
+      rc = run_upsample(e, U0, U1, N, H, W, st);
+      if (rc) return rc;
+    }
     {  // conv_up1 + lrelu
-      ConvIO io{U1, 64, N, 2 * H, 2 * W};
+      ConvIO io{e->opt_fold_up ? U0 : U1, 64, N, 2 * H, 2 * W, 0, e->opt_fold_up};
       ConvArgs a = base;
       a.slope = 0.2f;
       a.out = U2;
@@ -706,10 +714,12 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
       rc = launch_conv(e, e->layers[li++], EPI_ACT_BF16, io, a, st);
       if (rc) return rc;
     }
-    rc = run_upsample(e, U2, U3, N, 2 * H, 2 * W, st);
-    if (rc) return rc;
+    if (!e->opt_fold_up) {
+      rc = run_upsample(e, U2, U3, N, 2 * H, 2 * W, st);
+      if (rc) return rc;
+    }
     {  // conv_up2 + lrelu
-      ConvIO io{U3, 64, N, 4 * H, 4 * W};
+      ConvIO io{e->opt_fold_up ? U2 : U3, 64, N, 4 * H, 4 * W, 0, e->opt_fold_up};
       ConvArgs a = base;
       a.slope = 0.2f;
       a.out = U4;
@@ -1008,6 +1018,10 @@ int b200sr_set_option(b200sr_engine* e, const char* key, int value) {
   }
   if (!strcmp(key, "fused_rdb")) {
     e->opt_fused_rdb = value;
+    return B200SR_OK;
+  }
+  if (!strcmp(key, "fold_up")) {
+    e->opt_fold_up = value;
     return B200SR_OK;
   }
   if (!strcmp(key, "profile")) {  // 1: time every launch with CUDA events; read back with b200sr_get_profile

@@ -57,6 +57,9 @@ struct ConvArgs {
   float slope;            // leaky slope (EPI_ACT_BF16)
   int in_planes;          // 0: input chunk c = channels [64c, 64c+64) of one NHWC tensor.  P > 0: chunk-planar
                           // input, chunk c is its own [N][H][W][64] tensor and image n of it is TMA image c*N + n
+  int in_up2;             // the input is the nearest-2x upsampling of a tensor of half this conv's H and W, read
+                          // through the duplicated-pixel TMA view (tmap.h::tmap_encode_act_up2): box = 66 source
+                          // pixels = 132 rows starting at x0 - 2, so every tap view starts one row later
   int in_fp16;            // A (activations) and B (weights) are fp16 instead of bf16
   int out_fp16;           // 16-bit output tensor is fp16 instead of bf16
   __nv_bfloat16* out;     // 16-bit NHWC destination (bf16 or fp16 per out_fp16)
@@ -483,8 +486,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
         for (int y = -1; y <= TH; ++y) {
           mbar_wait(&bar_empty[stage], phase ^ 1);
           if (elect_one_sync()) {
-            mbar_arrive_expect_tx(&bar_full[stage], Cfg::A_BOX_BYTES);
-            if (args.in_planes)
+            mbar_arrive_expect_tx(&bar_full[stage], args.in_up2 ? 132 * 128 : Cfg::A_BOX_BYTES);
+            if (args.in_up2)   // rows y0+y = -1 and >= H map to source rows -1 and >= H/2: zero-filled
+              tma_load_5d(&amap, &bar_full[stage], sA + stage * Cfg::A_STAGE_BYTES, c * 64, 0, (x0 + 1) / 2 - 1,
+                          (y0 + y) >> 1, n);
+            else if (args.in_planes)
               tma_load_4d(&amap, &bar_full[stage], sA + stage * Cfg::A_STAGE_BYTES, 0, x0, y0 + y, c * args.N + n);
             else
               tma_load_4d(&amap, &bar_full[stage], sA + stage * Cfg::A_STAGE_BYTES, c * 64, x0, y0 + y, n);
@@ -528,7 +534,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
           mbar_wait(&bar_full[stage], phase);
           tc_fence_after();
           const uint32_t dcol = tmem_base + static_cast<uint32_t>((y - 1 + blk_lo) * COUT);
-          const uint64_t ad0 = adesc0 + static_cast<uint64_t>((stage * Cfg::A_STAGE_BYTES) >> 4);
+          const uint64_t ad0 = adesc0 + static_cast<uint64_t>((stage * Cfg::A_STAGE_BYTES + (args.in_up2 ? 128 : 0)) >> 4);
           const uint64_t bd0 = bdesc_w + static_cast<uint64_t>((blk_lo * COUT * 128) >> 4);
           const uint32_t idesc_n = nblk == 3 ? idesc3 : (nblk == 2 ? idesc2 : idesc1);
           if (elect_one_sync()) {

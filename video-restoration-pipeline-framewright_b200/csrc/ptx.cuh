@@ -87,6 +87,17 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
         "r"(c3)
       : "memory");
 }
+// 5-D variant (the duplicated-pixel view of conv_up's input, tmap.h::tmap_encode_act_up2)
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3), "r"(c4)
+      : "memory");
+}
 // Same with an L2 eviction policy (make_l2_policy_*)
 __device__ __forceinline__ void tma_load_4d_hint(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
                                                  int c2, int c3, uint64_t policy) {

@@ -48,4 +48,26 @@ inline bool tmap_encode_act(CUtensorMap* out, const void* base, int N, int H, in
   return r == CUDA_SUCCESS;
 }
 
+// Nearest-2x upsampled VIEW of a low-resolution NHWC tensor [N][H][W][Cpitch]: dims {C, 2, W, H, N} with a ZERO
+// stride on the second dimension, so a box {cbox, 2, boxw, 1, 1} lands in shared memory as 2*boxw pixel rows in
+// which every low-resolution pixel appears twice (F.interpolate(scale_factor=2, mode='nearest') along x; along y
+// the caller addresses row Y >> 1).  Out-of-bounds pixels/rows are zero-filled as in tmap_encode_act.  Verified on
+// B200 by csrc/tools/probe_dup.cu.
+inline bool tmap_encode_act_up2(CUtensorMap* out, const void* base, int N, int H, int W, int Cpitch, int cbox, int boxw,
+                                int swizzle_bytes) {
+  if (!tmap_init()) return false;
+  cuuint64_t dims[5] = {(cuuint64_t)Cpitch, 2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[4] = {0, (cuuint64_t)Cpitch * 2, (cuuint64_t)W * Cpitch * 2, (cuuint64_t)H * W * Cpitch * 2};
+  cuuint32_t box[5] = {(cuuint32_t)cbox, 2, (cuuint32_t)boxw, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = tmap_fn()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 }  // namespace b200sr
