@@ -83,7 +83,11 @@ int b200sr_upscale_host_u8(b200sr_engine* e, const uint8_t* src_host, uint8_t* d
 /* Number of kernels the last enqueue launched (bench.py reports it as gpu_launches). */
 int b200sr_last_launch_count(const b200sr_engine* e);
 
-/* Debug / measurement hooks (not part of the reference surface). */
+/* Debug / measurement hooks (not part of the reference surface).
+ * Options: "fused_rdb" (1: one persistent kernel per residual dense block; 0: five per-conv launches, same bytes),
+ * "fold_up" (1: conv_up1/up2 read the nearest-2x upsampling through the duplicated-pixel TMA view; 0: materialise it),
+ * "profile" (1: CUDA events around every launch, read with b200sr_get_profile), "force_th", "max_ctas",
+ * "rdb_off" / "rdb_order" (fused work-list schedule), "rdb_stats" (instrumented builds only). */
 int b200sr_set_option(b200sr_engine* e, const char* key, int value);
 
 /* Per-kernel-class timing collected while option "profile" is 1 (CUDA events around every launch).
