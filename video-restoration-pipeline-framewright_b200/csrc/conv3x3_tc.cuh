@@ -298,18 +298,11 @@ __device__ __forceinline__ void store_trunk_pair(__nv_bfloat16* hi_dst, uint8_t*
 // Shared by the per-conv kernel and the fused RDB kernel so that both produce the same bits.
 template <bool RRDB>
 __device__ __forceinline__ void trunk_pixel(const ConvArgs& a, const float* s_bias, float (&acc)[64],
-                                            const uint32_t (&hi)[4][8], const uint32_t (&lo)[2][8], int n, int y,
+                                            const uint32_t (&hi)[4][8], const uint32_t (&lo)[2][8],
+                                            const uint32_t (&h0)[4][8], const uint32_t (&l0)[2][8], int n, int y,
                                             int x) {
   const size_t pix = (static_cast<size_t>(n) * a.H + y) * a.W + x;
   const size_t loff = lo_off(n, y, x, a.H, a.W);
-  uint32_t h0[4][8], l0[2][8];
-  if constexpr (RRDB) {
-    const __nv_bfloat16* xh = a.xb_hi + pix * a.out_pitch;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) ld_global_256_ef(xh + g * 16, h0[g]);
-#pragma unroll
-    for (int g = 0; g < 2; ++g) ld_global_256_ef(a.xb_lo + loff + g * LO_GSTRIDE, l0[g]);
-  }
 #pragma unroll
   for (int g = 0; g < 2; ++g)
 #pragma unroll
@@ -331,6 +324,14 @@ __device__ __forceinline__ void trunk_pixel(const ConvArgs& a, const float* s_bi
       }
     }
   store_trunk_pair(a.out + pix * a.out_pitch + a.out_choff, a.lo_out + loff, acc);
+}
+// one pixel's pair (64 channels) from an NHWC hi tensor + the tile-interleaved lo bytes
+__device__ __forceinline__ void load_trunk_pair(const __nv_bfloat16* hi_px, const uint8_t* lo_px, uint32_t (&hi)[4][8],
+                                                uint32_t (&lo)[2][8]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) ld_global_256_ef(hi_px + g * 16, hi[g]);
+#pragma unroll
+  for (int g = 0; g < 2; ++g) ld_global_256_ef(lo_px + g * LO_GSTRIDE, lo[g]);
 }
 
 // Fused pointwise tail of one output pixel (one thread).
@@ -354,14 +355,11 @@ __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* s
     store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc, a.out_fp16);
   } else if constexpr (EPI == EPI_RDB5 || EPI == EPI_RDB5_RRDB) {
     static_assert(COUT == 64, "trunk epilogues are 64-channel");
-    uint32_t hi[4][8], lo[2][8];
-    const __nv_bfloat16* xh = a.hi_in + pix * a.out_pitch;
+    uint32_t hi[4][8], lo[2][8], h0[4][8], l0[2][8];
     const size_t loff = lo_off(n, y, x, a.H, a.W);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) ld_global_256_ef(xh + g * 16, hi[g]);
-#pragma unroll
-    for (int g = 0; g < 2; ++g) ld_global_256_ef(a.lo_in + loff + g * LO_GSTRIDE, lo[g]);
-    trunk_pixel<EPI == EPI_RDB5_RRDB>(a, s_bias, acc, hi, lo, n, y, x);
+    load_trunk_pair(a.hi_in + pix * a.out_pitch, a.lo_in + loff, hi, lo);
+    if constexpr (EPI == EPI_RDB5_RRDB) load_trunk_pair(a.xb_hi + pix * a.out_pitch, a.xb_lo + loff, h0, l0);
+    trunk_pixel<EPI == EPI_RDB5_RRDB>(a, s_bias, acc, hi, lo, h0, l0, n, y, x);
   } else if constexpr (EPI == EPI_ADD_F32) {
     const float* f = a.fadd + trunk_off(n, y, x, a.H, a.W);
 #pragma unroll

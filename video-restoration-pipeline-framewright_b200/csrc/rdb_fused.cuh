@@ -562,15 +562,17 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
         for (int Y = 0; Y < item.rows; ++Y) {
           const int sl = 2 * Y;
           if ((Y & 1) == eg) {
-            // fetch this pixel's x pair now, while the MMAs of the row are still in flight
-            uint32_t xh[4][8], xl[2][8];
+            // Request one of this pixel's pairs now, while the MMAs of the row are still in flight: the RDB input
+            // pair x, or at the RRDB end the RRDB input pair x0 -- x0 was last touched three launches ago and
+            // comes from DRAM, x is L2-warm (chunk-0 TMA loads, lo prefetch) and is fetched after the accumulators.
+            uint32_t ph[4][8], pl[2][8];
+            const size_t pix = (static_cast<size_t>(n) * L.H + item.y0 + Y) * L.W + x;
+            const size_t loff = lo_off(n, item.y0 + Y, x < L.W ? x : 0, L.H, L.W);
             if (x < L.W) {
-              const __nv_bfloat16* hp = L.hi_in + ((static_cast<size_t>(n) * L.H + item.y0 + Y) * L.W + x) * L.out_pitch;
-              const uint8_t* lp = L.lo_in + lo_off(n, item.y0 + Y, x, L.H, L.W);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) ld_global_256_ef(hp + g * 16, xh[g]);
-#pragma unroll
-              for (int g = 0; g < 2; ++g) ld_global_256_ef(lp + g * LO_GSTRIDE, xl[g]);
+              if (args.rrdb_end)
+                load_trunk_pair(L.xb_hi + pix * L.out_pitch, L.xb_lo + loff, ph, pl);
+              else
+                load_trunk_pair(L.hi_in + pix * L.out_pitch, L.lo_in + loff, ph, pl);
             }
             RDB_TIMED(0, mbar_wait(&bar_rfull[sl], (rfull_par >> sl) & 1u));
             if (q == 2 && lane == 0) RDB_STAMP2(it, Y, 1);
@@ -585,10 +587,13 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             }
             RDB_TIMED(2, {
               if (x < L.W && !(B200SR_ABL_NOEPI & 2)) {
-                if (args.rrdb_end)
-                  trunk_pixel<true>(L, s_bias[4], acc, xh, xl, n, item.y0 + Y, x);
-                else
-                  trunk_pixel<false>(L, s_bias[4], acc, xh, xl, n, item.y0 + Y, x);
+                if (args.rrdb_end) {
+                  uint32_t xh[4][8], xl[2][8];
+                  load_trunk_pair(L.hi_in + pix * L.out_pitch, L.lo_in + loff, xh, xl);
+                  trunk_pixel<true>(L, s_bias[4], acc, xh, xl, ph, pl, n, item.y0 + Y, x);
+                } else {
+                  trunk_pixel<false>(L, s_bias[4], acc, ph, pl, ph, pl, n, item.y0 + Y, x);
+                }
               }
             });
             RDB_COUNT(3, 1);
