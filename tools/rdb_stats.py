@@ -14,7 +14,7 @@ from framewright_b200.archs import make_synthetic_state_dict  # noqa: E402
 from framewright_b200.engine import B200Engine  # noqa: E402
 
 N, H, W = (int(v) for v in sys.argv[1:4]) if len(sys.argv) > 3 else (1, 720, 1280)
-model = "RealESRGAN_x4plus_anime_6B"
+model = os.environ.get("MODEL", "RealESRGAN_x4plus_anime_6B")   # LAUNCH < 0: counters only, no trace stamps
 eng = B200Engine(model, make_synthetic_state_dict(model, 0), gpu_id=0)
 x = torch.from_numpy(np.random.default_rng(0).integers(0, 256, size=(N, H, W, 3), dtype=np.uint8)).cuda()
 eng.upscale_device(x)

@@ -10,7 +10,8 @@ from framewright_b200.engine import B200Engine
 model = "RealESRGAN_x4plus"
 eng = B200Engine(model, make_synthetic_state_dict(model, 0), gpu_id=0)
 rng = np.random.default_rng(0)
-def run(N, offs, reps=2):
+def run(N, offs, reps=2, inter=0):
+    eng.set_option("rdb_interleave", inter)
     x = torch.from_numpy(rng.integers(0, 256, size=(N, 720, 1280, 3), dtype=np.uint8)).cuda()
     eng.set_option("rdb_off", offs[0] + 100*offs[1] + 10000*offs[2] + 1000000*offs[3])
     for _ in range(2): y = eng.upscale_device(x)
@@ -20,10 +21,12 @@ def run(N, offs, reps=2):
     for _ in range(reps): y = eng.upscale_device(x)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    print(f"N={N} off={offs}: {ms:8.2f} ms/step  {N/ms*1e3:6.2f} frames/s", flush=True)
-for offs in [(1,2,3,5), (1,2,3,4), (1,2,4,6), (1,1,2,3), (1,2,2,4), (2,3,4,6), (1,2,3,6)]:
-    run(4, offs)
-for N in (2, 6, 8):
-    run(N, (1,2,3,5))
+    print(f"N={N} off={offs} interleave={inter}: {ms:8.2f} ms/step  {N/ms*1e3:6.2f} frames/s", flush=True)
+run(4, (1,2,3,5))
+for offs in [(1,2,3,5), (1,2,3,4), (1,1,2,3), (1,1,2,2), (0,1,1,2), (1,2,4,6)]:
+    run(4, offs, inter=1)
+run(8, (1,2,3,5), inter=1)
+run(8, (1,1,2,3), inter=1)
+run(2, (1,2,3,5), inter=1)
 run(4, (1,2,3,5))
 eng.close()

@@ -360,7 +360,8 @@ int ensure_ws(b200sr_engine* e, size_t bytes, cudaStream_t st) {
 // ---- fused RDB: item table (skewed row strips) ------------------------------------------------------
 constexpr int RDB_STRIP = 16;   // rows per strip (= rows per conv1..4 item; conv5 items have 8)
 int RDB_ORDER[5] = {0, 1, 2, 3, 4};      // order of the convs inside one step of the work list (option rdb_order)
-int RDB_STEP_OFF[5] = {0, 1, 2, 3, 5};   // step in which conv k reaches strip s: s + RDB_STEP_OFF[k] (option rdb_off)
+int RDB_STEP_OFF[5] = {0, 1, 2, 3, 5};
+int RDB_INTERLEAVE = 0;                  // option rdb_interleave   // step in which conv k reaches strip s: s + RDB_STEP_OFF[k] (option rdb_off)
 
 // Strip s of conv k covers rows [16 s - 8 k, 16 s + 16 - 8 k): every conv is shifted up by 8 rows relative to
 // its predecessor, so the rows an item reads (its own +-1) of a lower conv belong to items earlier in the list.
@@ -370,9 +371,14 @@ void build_rdb_items(int N, int H, int W, std::vector<RdbItem>& items, int* nfla
   const int nblk = (H + 7) / 8;
   *nflags = N * 4 * nblk;
   items.clear();
-  for (int n = 0; n < N; ++n)
-    for (int t = 0; t < S + RDB_STEP_OFF[4]; ++t)
+  // RDB_INTERLEAVE = 0: frame after frame.  1: all frames advance together (step-major): N times more independent
+  // items per step, i.e. N times more time between a producer item and its consumers, for an N times larger
+  // L2 working set.
+  for (int outer = 0; outer < (RDB_INTERLEAVE ? S + RDB_STEP_OFF[4] : N); ++outer)
+    for (int inner = 0; inner < (RDB_INTERLEAVE ? N : S + RDB_STEP_OFF[4]); ++inner)
       for (int kk = 0; kk < 5; ++kk) {
+        const int n = RDB_INTERLEAVE ? inner : outer;
+        const int t = RDB_INTERLEAVE ? outer : inner;
         // within a step all groups are independent; the natural order conv1..conv5 measured best (rdb_sweep.py)
         const int k = RDB_ORDER[kk];
         // in step t conv k works on strip t - RDB_STEP_OFF[k]: its producer ran one or two steps (~60 items each)
@@ -475,7 +481,12 @@ int launch_rdb_fused(b200sr_engine* e, int li, bool rrdb_end, __nv_bfloat16* Dcu
   a.counter = e->d_rdb_flags + e->rdb_nflags;
   a.flag_target = ((W + 127) / 128) * RDB_NEPI_WARPS;
   a.rrdb_end = rrdb_end ? 1 : 0;
-  if (++e->rdb_launch_idx == e->opt_rdb_stats) {
+  ++e->rdb_launch_idx;
+  if (e->rdb_launch_idx == -e->opt_rdb_stats) {   // negative: cycle counters only (no per-item / per-row stamps)
+    if (!e->d_rdb_stats) CUDA_TRY(e, cudaMalloc(&e->d_rdb_stats, 148 * 16 * sizeof(long long)));
+    a.stats = e->d_rdb_stats;
+  }
+  if (e->rdb_launch_idx == e->opt_rdb_stats) {
     if (!e->d_rdb_stats) CUDA_TRY(e, cudaMalloc(&e->d_rdb_stats, 148 * 16 * sizeof(long long)));
     a.stats = e->d_rdb_stats;
     if (!e->d_rdb_trace) CUDA_TRY(e, cudaMalloc(&e->d_rdb_trace, static_cast<size_t>(e->rdb_nitems) * 10 * sizeof(long long)));
@@ -1001,6 +1012,11 @@ int b200sr_set_option(b200sr_engine* e, const char* key, int value) {
     RDB_STEP_OFF[3] = (value / 10000) % 100;
     RDB_STEP_OFF[4] = (value / 1000000) % 100;
     e->rdb_n = 0;   // rebuild the work list
+    return B200SR_OK;
+  }
+  if (!strcmp(key, "rdb_interleave")) {
+    RDB_INTERLEAVE = value;
+    e->rdb_n = -1;   // rebuild the work list
     return B200SR_OK;
   }
   if (!strcmp(key, "rdb_order")) {   // five decimal digits, e.g. 32104

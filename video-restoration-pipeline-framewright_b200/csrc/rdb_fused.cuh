@@ -245,35 +245,37 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             bulk_load_1d(&bar_wfull[wb], sW + wb * RDB_WBUF_BYTES + d * wtile, wsrc + d * wtile, wtile);
         }
         __syncwarp();
-        // The 8-row blocks of the predecessor conv this chunk reads (rows y0-1 .. y0+rows, at most 4 blocks) must
-        // be complete.  One batch of relaxed loads (the common case: all complete), then ONE acquire fence and
-        // one generic->async proxy fence before the TMA loads of the chunk's rows (the weights, which do not depend
-        // on other CTAs, are already in flight).
-        const int dep = (c > 0) ? item.dep_base[c - 1] : -1;
-        if (dep >= 0 && !B200SR_ABL_NODEP) {
+        // The 8-row blocks of the predecessor conv this chunk reads (rows y0-1 .. y0+rows, at most 4 blocks) must be
+        // complete -- checked LAZILY, block by block, as the row loop reaches them: the lower blocks were produced
+        // two steps ago and are ready, the upper ones belong to an item that may still be running, and its last
+        // block is needed only for this chunk's final (halo) row.  First one batch of relaxed loads for the blocks
+        // that are already complete, then ONE acquire fence + one generic->async proxy fence per wait before the
+        // TMA loads that depend on it (the weights, which do not depend on other CTAs, are already in flight).
+        const int dep = (c > 0 && !B200SR_ABL_NODEP) ? item.dep_base[c - 1] : -1;
+        int ready_blk = 1 << 30;   // highest 8-row block of the predecessor known complete (and fenced)
+        if (dep >= 0) {
           RDB_STAMP(it, 2 * c - 1);
+          const int bl = (item.y0 > 0 ? item.y0 - 1 : 0) >> 3;
+          const int r_hi = item.y0 + item.rows < L.H ? item.y0 + item.rows : L.H - 1;
+          const int nb = (r_hi >> 3) - bl + 1;
+          int m = 0;   // leading complete blocks
           RDB_TIMED(4, {
-            if (elect_one_sync()) {
-              const int bl = (item.y0 > 0 ? item.y0 - 1 : 0) >> 3;
-              const int r_hi = item.y0 + item.rows < L.H ? item.y0 + item.rows : L.H - 1;
-              const int nb = (r_hi >> 3) - bl + 1;
+            if (lane == 0) {
               const int* f = args.flags + dep + bl;
               int v[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) v[j] = j < nb ? ld_relaxed_gpu(f + j) : args.flag_target;
-              while (v[0] < args.flag_target || v[1] < args.flag_target || v[2] < args.flag_target ||
-                     v[3] < args.flag_target) {
-                __nanosleep(64);
+              for (int j2 = 0; j2 < 4; ++j2) v[j2] = j2 < nb ? ld_relaxed_gpu(f + j2) : args.flag_target;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (j < nb && v[j] < args.flag_target) v[j] = ld_relaxed_gpu(f + j);
+              for (int j2 = 0; j2 < 4; ++j2)
+                if (m == j2 && j2 < nb && v[j2] >= args.flag_target) m = j2 + 1;
+              if (m > 0) {
+                fence_acq_rel_gpu();
+                fence_proxy_async_global();
               }
-              fence_acq_rel_gpu();
-              fence_proxy_async_global();
             }
-            __syncwarp();
+            m = __shfl_sync(0xffffffffu, m, 0);
           });
-          RDB_STAMP(it, 2 * c);
+          ready_blk = bl + m - 1;
         }
         // x.hi (chunk 0) is read by all five convs, ~5 steps apart, with ~100 MB of other traffic in between: keep
         // it in L2 (evict_last) until conv5, its last reader, has passed (evict_first)
@@ -284,8 +286,20 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
 #endif
         for (int y = -1; y <= item.rows; ++y) {
           const int r = item.y0 + y;
+          if (r >= 0 && r < L.H && (r >> 3) > ready_blk) {   // first row of a block not yet known complete
+            RDB_TIMED(4, {
+              if (lane == 0) {
+                const int* f = args.flags + dep + (r >> 3);
+                while (ld_relaxed_gpu(f) < args.flag_target) __nanosleep(64);
+                fence_acq_rel_gpu();
+                fence_proxy_async_global();
+              }
+              __syncwarp();
+            });
+            ready_blk = r >> 3;
+          }
           RDB_TIMED(1, mbar_wait(&bar_empty[stage], phase ^ 1));
-          if (elect_one_sync()) {
+          if (lane == 0) {   // (the lane that executed the fences above)
             mbar_arrive_expect_tx(&bar_full[stage], 130 * 128);
             tma_load_4d_hint(&amap, &bar_full[stage], sA + stage * RDB_A_STAGE_BYTES, 0, x0, r, c * L.N + item.n, pol);
           }
