@@ -116,6 +116,8 @@ int b200sr_debug_choose_th(int coutp, int n, int h, int w, int num_sms);
 /* rdb_items: work list of the fused-RDB kernel; 8 ints per item: k n y0 rows tx flag_base dep_base0 dep_base1
  * (counter of 8-row block b of a conv = base + b).  Returns the item count. */
 int b200sr_debug_rdb_items(int n, int h, int w, int* out, int max_items);
+/* Output rows per completion counter of the fused-RDB schedule (flag_base / dep_base index blocks of this many rows). */
+int b200sr_debug_rdb_flag_rows(void);
 
 /* Test hook: one tensor-core 3x3 conv layer on caller-provided device tensors (bf16 NHWC in/out,
  * fp32 OIHW host weights).  epi 0: leaky(slope) ; epi 1: PReLU(prelu_host[64]); fp16 != 0: tensors and

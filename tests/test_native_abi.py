@@ -138,7 +138,7 @@ def test_choose_th_bounds(native_lib):
 @pytest.mark.parametrize("n,h,w", [(1, 720, 1280), (2, 45, 300), (1, 16, 128), (1, 7, 50), (1, 333, 517)])
 def test_fused_rdb_work_list(native_lib, n, h, w):
     """Work list of the fused-RDB kernel: every (conv, frame, row, column) is covered exactly once, item row
-    ranges start on 8-row block boundaries (completion counters are per block), and every 8-row block an item
+    ranges start on 8-row boundaries (a multiple of the completion-counter block), and every counter block an item
     reads from a lower conv (its own rows +-1) is produced entirely by EARLIER items of the list -- so in-order
     round-robin execution on co-resident CTAs cannot deadlock."""
     cap = 200000
@@ -147,7 +147,9 @@ def test_fused_rdb_work_list(native_lib, n, h, w):
     assert 0 < cnt <= cap
     items = np.frombuffer(buf, dtype=np.int32, count=cnt * 8).reshape(cnt, 8)
     xt = (w + 127) // 128
-    nblk = (h + 7) // 8
+    fr = native_lib.b200sr_debug_rdb_flag_rows()
+    assert fr in (4, 8)
+    nblk = (h + fr - 1) // fr
     cover = np.zeros((5, n, h, xt), np.int32)
     last_writer = np.full((n, 4, nblk), -1, np.int64)     # index of the last item that stores into the block
     for i, (k, fn, y0, rows, tx, fb, d0, d1) in enumerate(items):
@@ -156,7 +158,7 @@ def test_fused_rdb_work_list(native_lib, n, h, w):
         cover[k, fn, y0:y0 + rows, tx] += 1
         if k < 4:
             assert fb == (fn * 4 + k) * nblk
-            for b in range(y0 // 8, (y0 + rows - 1) // 8 + 1):
+            for b in range(y0 // fr, (y0 + rows - 1) // fr + 1):
                 last_writer[fn, k, b] = i
         else:
             assert fb == -1
@@ -170,4 +172,4 @@ def test_fused_rdb_work_list(native_lib, n, h, w):
             dep = min(2 * c - 1, k - 1)
             assert dbase == (fn * 4 + dep) * nblk
             for r in range(max(y0 - 1, 0), min(y0 + rows + 1, h)):
-                assert 0 <= last_writer[fn, dep, r // 8] < i, (i, k, r)
+                assert 0 <= last_writer[fn, dep, r // fr] < i, (i, k, r)

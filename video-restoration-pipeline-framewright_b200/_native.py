@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "b200sr_set_prelu", "b200sr_finalize", "b200sr_output_dims", "b200sr_workspace_bytes",
     "b200sr_enqueue_u8", "b200sr_upscale_host_u8", "b200sr_last_launch_count", "b200sr_set_option",
     "b200sr_last_error", "b200sr_version", "b200sr_debug_conv3x3", "b200sr_get_profile",
-    "b200sr_debug_plan_regions", "b200sr_debug_pack_weights", "b200sr_debug_choose_th", "b200sr_debug_rdb_items", "b200sr_debug_rdb_stats", "b200sr_debug_rdb_trace",
+    "b200sr_debug_plan_regions", "b200sr_debug_pack_weights", "b200sr_debug_choose_th", "b200sr_debug_rdb_items", "b200sr_debug_rdb_flag_rows", "b200sr_debug_rdb_stats", "b200sr_debug_rdb_trace",
 ]
 
 OK, ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_STATE = 0, 1, 2, 3, 4
@@ -149,6 +149,8 @@ def load() -> ctypes.CDLL:
         lib.b200sr_debug_choose_th.restype = c_int
         lib.b200sr_debug_rdb_items.argtypes = [c_int, c_int, c_int, ctypes.POINTER(c_int), c_int]
         lib.b200sr_debug_rdb_items.restype = c_int
+        lib.b200sr_debug_rdb_flag_rows.argtypes = []
+        lib.b200sr_debug_rdb_flag_rows.restype = c_int
         lib.b200sr_debug_rdb_stats.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_longlong), c_int]
         lib.b200sr_debug_rdb_stats.restype = c_int
         lib.b200sr_debug_rdb_trace.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_longlong), c_int]

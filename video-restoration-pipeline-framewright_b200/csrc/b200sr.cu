@@ -368,7 +368,7 @@ int RDB_INTERLEAVE = 0;                  // option rdb_interleave   // step in w
 void build_rdb_items(int N, int H, int W, std::vector<RdbItem>& items, int* nflags) {
   const int S = (H + 32 + RDB_STRIP - 1) / RDB_STRIP;
   const int xt = (W + 127) / 128;
-  const int nblk = (H + 7) / 8;
+  const int nblk = (H + RDB_FLAG_ROWS - 1) / RDB_FLAG_ROWS;   // completion counters per conv and frame
   *nflags = N * 4 * nblk;
   items.clear();
   // RDB_INTERLEAVE = 0: frame after frame.  1: all frames advance together (step-major): N times more independent
@@ -1124,6 +1124,8 @@ long long b200sr_debug_pack_weights(const float* weight, int cout, int cin, int 
 
 // The fused-RDB work list for n frames of h x w: 8 ints per item (k n y0 rows tx flag_base dep_base[0] dep_base[1]);
 // returns the item count (may exceed max_items).
+int b200sr_debug_rdb_flag_rows(void) { return RDB_FLAG_ROWS; }
+
 int b200sr_debug_rdb_items(int n, int h, int w, int* out, int max_items) {
   if (n <= 0 || h <= 0 || w <= 0) return -1;
   std::vector<RdbItem> items;

@@ -41,7 +41,7 @@ struct RdbItem {      // 32 bytes, built on the host (b200sr.cu::build_rdb_items
   int y0;             // first output row
   int rows;           // output rows in this item (<= 16 for k < 4, <= 8 for k == 4)
   int tx;             // 128-pixel column
-  int flag_base;      // index of the completion counter of 8-row block 0 of (n, k); -1 for conv5
+  int flag_base;      // index of the completion counter of block 0 of (n, k); -1 for conv5
   int dep_base[2];    // per dependent chunk (c = 1, 2): counter base of the conv whose output that chunk needs
                       // (-1 = none); block b's counter is dep_base + b
 };
@@ -50,7 +50,7 @@ struct RdbArgs {
   ConvArgs L[5];          // per-conv parameters (wpack, bias, nchunks, last_ksteps, out/out_choff, xa/xb, ...)
   const RdbItem* items;
   int nitems;
-  int* flags;             // [frame][conv1..4][8-row block], zeroed before the launch
+  int* flags;             // [frame][conv1..4][block], zeroed before the launch
   int* counter;           // next unclaimed item (zeroed before the launch): items are claimed in list order
   int flag_target;        // counter value of a complete block: column tiles x epilogue warps
   int rrdb_end;           // conv5 epilogue also applies the RRDB-level skip
@@ -125,6 +125,12 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 #endif
 
 constexpr int RDB_QD = 2;
+#ifndef B200SR_RDB_FLAG_SHIFT
+#define B200SR_RDB_FLAG_SHIFT 3
+#endif
+constexpr int RDB_FLAG_SHIFT = B200SR_RDB_FLAG_SHIFT;   // completion counters per 2^shift output rows of a conv
+constexpr int RDB_FLAG_ROWS = 1 << RDB_FLAG_SHIFT;
+constexpr int RDB_MAX_DEP_BLOCKS = 18 / RDB_FLAG_ROWS + 2;
 constexpr int RDB_NSTAGES = 4;
 constexpr int RDB_WBUF_BYTES = 9 * 64 * 128;                 // weight chunk buffer sized for Cout = 64
 constexpr int RDB_A_STAGE_BYTES = 17 * 1024;
@@ -245,28 +251,28 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             bulk_load_1d(&bar_wfull[wb], sW + wb * RDB_WBUF_BYTES + d * wtile, wsrc + d * wtile, wtile);
         }
         __syncwarp();
-        // The 8-row blocks of the predecessor conv this chunk reads (rows y0-1 .. y0+rows, at most 4 blocks) must be
+        // The blocks of the predecessor conv this chunk reads (rows y0-1 .. y0+rows, at most 4 blocks) must be
         // complete -- checked LAZILY, block by block, as the row loop reaches them: the lower blocks were produced
         // two steps ago and are ready, the upper ones belong to an item that may still be running, and its last
         // block is needed only for this chunk's final (halo) row.  First one batch of relaxed loads for the blocks
         // that are already complete, then ONE acquire fence + one generic->async proxy fence per wait before the
         // TMA loads that depend on it (the weights, which do not depend on other CTAs, are already in flight).
         const int dep = (c > 0 && !B200SR_ABL_NODEP) ? item.dep_base[c - 1] : -1;
-        int ready_blk = 1 << 30;   // highest 8-row block of the predecessor known complete (and fenced)
+        int ready_blk = 1 << 30;   // highest block of the predecessor known complete (and fenced)
         if (dep >= 0) {
           RDB_STAMP(it, 2 * c - 1);
-          const int bl = (item.y0 > 0 ? item.y0 - 1 : 0) >> 3;
+          const int bl = (item.y0 > 0 ? item.y0 - 1 : 0) >> RDB_FLAG_SHIFT;
           const int r_hi = item.y0 + item.rows < L.H ? item.y0 + item.rows : L.H - 1;
-          const int nb = (r_hi >> 3) - bl + 1;
+          const int nb = (r_hi >> RDB_FLAG_SHIFT) - bl + 1;
           int m = 0;   // leading complete blocks
           RDB_TIMED(4, {
             if (lane == 0) {
               const int* f = args.flags + dep + bl;
-              int v[4];
+              int v[RDB_MAX_DEP_BLOCKS];
 #pragma unroll
-              for (int j2 = 0; j2 < 4; ++j2) v[j2] = j2 < nb ? ld_relaxed_gpu(f + j2) : args.flag_target;
+              for (int j2 = 0; j2 < RDB_MAX_DEP_BLOCKS; ++j2) v[j2] = j2 < nb ? ld_relaxed_gpu(f + j2) : args.flag_target;
 #pragma unroll
-              for (int j2 = 0; j2 < 4; ++j2)
+              for (int j2 = 0; j2 < RDB_MAX_DEP_BLOCKS; ++j2)
                 if (m == j2 && j2 < nb && v[j2] >= args.flag_target) m = j2 + 1;
               if (m > 0) {
                 fence_acq_rel_gpu();
@@ -286,17 +292,17 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
 #endif
         for (int y = -1; y <= item.rows; ++y) {
           const int r = item.y0 + y;
-          if (r >= 0 && r < L.H && (r >> 3) > ready_blk) {   // first row of a block not yet known complete
+          if (r >= 0 && r < L.H && (r >> RDB_FLAG_SHIFT) > ready_blk) {   // first row of a block not yet known complete
             RDB_TIMED(4, {
               if (lane == 0) {
-                const int* f = args.flags + dep + (r >> 3);
+                const int* f = args.flags + dep + (r >> RDB_FLAG_SHIFT);
                 while (ld_relaxed_gpu(f) < args.flag_target) __nanosleep(64);
                 fence_acq_rel_gpu();
                 fence_proxy_async_global();
               }
               __syncwarp();
             });
-            ready_blk = r >> 3;
+            ready_blk = r >> RDB_FLAG_SHIFT;
           }
           RDB_TIMED(1, mbar_wait(&bar_empty[stage], phase ^ 1));
           if (lane == 0) {   // (the lane that executed the fences above)
@@ -634,12 +640,12 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             if (q == 2 && lane == 0) RDB_STAMP2(it, Y, 2);
           }
           rfull_par ^= 1u << Y;
-          // publish an 8-row block once this warp has stored its rows of it (item.y0 is a multiple of 8); the
+          // publish an block once this warp has stored its rows of it (item.y0 is a multiple of 8); the
           // block is complete when every epilogue warp of every column tile has added 1
-          if ((Y & 7) == 7 || Y == item.rows - 1) {
+          if ((Y & (RDB_FLAG_ROWS - 1)) == RDB_FLAG_ROWS - 1 || Y == item.rows - 1) {
             RDB_TIMED(7, {
               __syncwarp();   // orders every lane's stores before lane 0's release (cumulative at gpu scope)
-              if (lane == 0) red_release_gpu_add(args.flags + item.flag_base + ((item.y0 + Y) >> 3), 1);
+              if (lane == 0) red_release_gpu_add(args.flags + item.flag_base + ((item.y0 + Y) >> RDB_FLAG_SHIFT), 1);
             });
           }
         }
