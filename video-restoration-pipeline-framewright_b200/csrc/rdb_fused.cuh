@@ -4,30 +4,27 @@
 // dense-block intermediates x1..x4 are produced and consumed while still resident in the 126 MB L2.
 //
 // Why: un-fused, every conv of an RDB re-reads the whole dense buffer from HBM; at 720p that is 1.8 KB of
-// DRAM traffic per pixel per RDB and puts all five convs below the roofline ridge.
+// DRAM traffic per pixel per RDB and puts all five convs below the roofline ridge (DESIGN.md sections 4.4, 6).
 //
-// How: the work is cut into items (conv k, 128-pixel column tx, 16 rows; 8 rows for conv5) and ordered strip by
-// strip: within strip s the items of conv1 come first, then conv2 (shifted UP by 8 rows relative to conv1),
-// conv3 (by 16) ... conv5 (by 32), so everything an item reads from a lower conv is produced by items that
-// precede it in the list, at most ~70 image rows (< 40 MB of bf16) earlier.  Items are dealt round-robin to
-// the resident CTAs; a CTA executes its items in order with the same TMA -> tcgen05 -> epilogue pipeline as
-// conv3x3_tc_kernel (per-item layer parameters).  Cross-CTA dependencies are completion counters per
-// (frame, conv, block of 8 rows) in global memory: epilogue warps release (threadfence + atomicAdd) when
-// their rows of a block are stored; the TMA producer of a consuming item acquires (ld.acquire.gpu +
-// fence.proxy.async) before it loads an input row of the first channel chunk that contains the
-// predecessor's output.  That is the LAST chunk of the item, and the predecessor's rows also complete during
-// ITS last chunk, so producer and consumer items that start together stream row-block by row-block with
-// little waiting.  All CTAs are co-resident (grid <= #SMs, 1 CTA/SM) and dependencies always point to
-// lower-numbered items, so the schedule cannot deadlock.
+// How: the work is cut into items (conv k, frame, 128-pixel column tx, 16 rows; 8 rows for conv5).  Strip s of
+// conv k covers rows [16 s - 8 k, 16 s + 16 - 8 k): every conv is shifted UP by 8 rows against its predecessor,
+// so everything an item reads from a lower conv (its own rows +- 1) is produced by items of earlier strips.  The
+// host orders the list by step t, conv k working on strip t - RDB_STEP_OFF[k] (b200sr.cu::build_rdb_items).
+// Items are CLAIMED dynamically in list order (one atomicAdd by the producer warp when it is ready to start the
+// item), so an item never starts before a lower-numbered one; a CTA runs its items with the same TMA ->
+// tcgen05 -> epilogue pipeline as conv3x3_tc_kernel (per-item layer parameters).  Cross-CTA dependencies are
+// completion counters per (frame, conv, block of RDB_FLAG_ROWS rows) in global memory: an epilogue warp does
+// __syncwarp + red.release.gpu.add once its rows of a block are stored; the TMA producer of a consuming item
+// polls the counters of the blocks a dependent channel chunk reads with relaxed loads -- lazily, when the row
+// loop reaches a block -- and then executes fence.acq_rel.gpu + fence.proxy.async.global before the TMA loads
+// that depend on it.  Dependencies always point to lower-numbered, i.e. already claimed and running, items, so
+// the schedule cannot deadlock, whatever the number of resident CTAs.
 #pragma once
 #include "conv3x3_tc.cuh"
 
 // timing ablations (tools only; results are wrong when set): skip the epilogue math + stores / the dependency waits
 #ifndef B200SR_ABL_NOEPI
 #define B200SR_ABL_NOEPI 0
-#endif
-#ifndef B200SR_ABL_NOPREFETCH
-#define B200SR_ABL_NOPREFETCH 1   // measured: no gain (2126 vs 2068 us per launch at 4 x 720p), off
 #endif
 #ifndef B200SR_ABL_NODEP
 #define B200SR_ABL_NODEP 0
@@ -47,7 +44,7 @@ struct RdbItem {      // 32 bytes, built on the host (b200sr.cu::build_rdb_items
 };
 
 struct RdbArgs {
-  ConvArgs L[5];          // per-conv parameters (wpack, bias, nchunks, last_ksteps, out/out_choff, xa/xb, ...)
+  ConvArgs L[5];          // per-conv parameters (wpack, bias, nchunks, last_ksteps, out/out_choff, residual pair, ...)
   const RdbItem* items;
   int nitems;
   int* flags;             // [frame][conv1..4][block], zeroed before the launch
@@ -235,11 +232,6 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
       const uint64_t pol_item = pol_normal;
 #else
       const uint64_t pol_item = item.k == 4 ? pol_first : pol_normal;
-#endif
-#if !B200SR_ABL_NOPREFETCH
-      // Chunk 0 is x.hi, written by the PREVIOUS launch and (for its first reader) still in DRAM: start all of the
-      // item's chunk-0 rows towards L2 now, one box per lane; the 4-stage ring alone covers only ~4 rows of latency.
-      if (lane < item.rows + 2) tma_prefetch_4d(&amap, 0, x0, item.y0 - 1 + lane, item.n);   // plane 0
 #endif
       for (int c = 0; c < L.nchunks; ++c) {
         RDB_TIMED(2, mbar_wait(&bar_wempty[wb], wphase ^ 1));
