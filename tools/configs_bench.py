@@ -23,8 +23,13 @@ CFGS = [
     ("animevideov3", "realesr-animevideov3", 16, 720, 1280, dict()),
 ]
 rng = np.random.default_rng(0)
+INTER = int(os.environ.get("INTERLEAVE", "-1"))
 for tag, model, N, H, W, kw in CFGS:
+    if os.environ.get("ONLY") and tag not in os.environ["ONLY"].split(","):
+        continue
     eng = B200Engine(model, make_synthetic_state_dict(model, 0), gpu_id=0)
+    if INTER >= 0:
+        eng.set_option("rdb_interleave", INTER)
     x = torch.from_numpy(rng.integers(0, 256, size=(N, H, W, 3), dtype=np.uint8)).cuda()
     for _ in range(2):
         y = eng.upscale_device(x, **kw)

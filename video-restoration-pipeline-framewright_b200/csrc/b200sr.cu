@@ -361,7 +361,7 @@ int ensure_ws(b200sr_engine* e, size_t bytes, cudaStream_t st) {
 constexpr int RDB_STRIP = 16;   // rows per strip (= rows per conv1..4 item; conv5 items have 8)
 int RDB_ORDER[5] = {0, 1, 2, 3, 4};      // order of the convs inside one step of the work list (option rdb_order)
 int RDB_STEP_OFF[5] = {0, 1, 2, 3, 5};
-int RDB_INTERLEAVE = 0;                  // option rdb_interleave   // step in which conv k reaches strip s: s + RDB_STEP_OFF[k] (option rdb_off)
+int RDB_INTERLEAVE = -1;                 // option rdb_interleave (build_rdb_items)   // step in which conv k reaches strip s: s + RDB_STEP_OFF[k] (option rdb_off)
 
 // Strip s of conv k covers rows [16 s - 8 k, 16 s + 16 - 8 k): every conv is shifted up by 8 rows relative to
 // its predecessor, so the rows an item reads (its own +-1) of a lower conv belong to items earlier in the list.
@@ -371,14 +371,17 @@ void build_rdb_items(int N, int H, int W, std::vector<RdbItem>& items, int* nfla
   const int nblk = (H + RDB_FLAG_ROWS - 1) / RDB_FLAG_ROWS;   // completion counters per conv and frame
   *nflags = N * 4 * nblk;
   items.clear();
-  // RDB_INTERLEAVE = 0: frame after frame.  1: all frames advance together (step-major): N times more independent
-  // items per step, i.e. N times more time between a producer item and its consumers, for an N times larger
-  // L2 working set.
-  for (int outer = 0; outer < (RDB_INTERLEAVE ? S + RDB_STEP_OFF[4] : N); ++outer)
-    for (int inner = 0; inner < (RDB_INTERLEAVE ? N : S + RDB_STEP_OFF[4]); ++inner)
+  // Frames advance through the list in groups of G: inside a group all frames take step t together (G times more
+  // independent items per step, i.e. G times more time between a producer item and its consumers), groups follow
+  // each other.  The L2 working set grows with G x frame width, so G is chosen to keep ~64 items per step: 1 at
+  // 720p (10 column tiles; interleaving measured 8 % slower there), 5 for 256-pixel-wide frames (+33 %), 2 for
+  // 512-pixel tiles (+12 %).  Option rdb_interleave: -1 auto, 0 off, G > 0 explicit.
+  const int G = RDB_INTERLEAVE < 0 ? std::max(1, std::min(N, (64 + 3 * xt) / (6 * xt)))
+                                   : (RDB_INTERLEAVE == 0 ? 1 : std::min(N, RDB_INTERLEAVE));
+  for (int g0 = 0; g0 < N; g0 += G)
+    for (int t = 0; t < S + RDB_STEP_OFF[4]; ++t)
+      for (int n = g0; n < std::min(N, g0 + G); ++n)
       for (int kk = 0; kk < 5; ++kk) {
-        const int n = RDB_INTERLEAVE ? inner : outer;
-        const int t = RDB_INTERLEAVE ? outer : inner;
         // within a step all groups are independent; the natural order conv1..conv5 measured best (rdb_sweep.py)
         const int k = RDB_ORDER[kk];
         // in step t conv k works on strip t - RDB_STEP_OFF[k]: its producer ran one or two steps (~60 items each)
