@@ -22,6 +22,6 @@ def run(N, offs, reps=2, inter=0):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     print(f"N={N} off={offs} interleave={inter}: {ms:8.2f} ms/step  {N/ms*1e3:6.2f} frames/s", flush=True)
-for offs in [(1,2,3,5), (1,2,3,4), (1,1,2,3), (1,2,2,4), (1,2,2,3), (1,1,2,4), (1,2,4,6), (0,1,2,3), (1,2,3,5)]:
-    run(4, offs)
+for N in (4, 6, 8, 12, 4, 8):
+    run(N, (1,2,3,5), inter=-1)
 eng.close()
