@@ -121,7 +121,13 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
   } while (0)
 #endif
 
-constexpr int RDB_QD = 2;
+#ifndef B200SR_RDB_QD
+#define B200SR_RDB_QD 2
+#endif
+#ifndef B200SR_RDB_POLL_NS
+#define B200SR_RDB_POLL_NS 64
+#endif
+constexpr int RDB_QD = B200SR_RDB_QD;
 #ifndef B200SR_RDB_FLAG_SHIFT
 #define B200SR_RDB_FLAG_SHIFT 3
 #endif
@@ -288,7 +294,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             RDB_TIMED(4, {
               if (lane == 0) {
                 const int* f = args.flags + dep + (r >> RDB_FLAG_SHIFT);
-                while (ld_relaxed_gpu(f) < args.flag_target) __nanosleep(64);
+                while (ld_relaxed_gpu(f) < args.flag_target) __nanosleep(B200SR_RDB_POLL_NS);
                 fence_acq_rel_gpu();
                 fence_proxy_async_global();
               }
