@@ -80,6 +80,13 @@ int b200sr_enqueue_u8(b200sr_engine* e, const uint8_t* src_dev, uint8_t* dst_dev
 int b200sr_upscale_host_u8(b200sr_engine* e, const uint8_t* src_host, uint8_t* dst_host, int n, int h, int w,
                            int tile, int tile_pad, int pre_pad);
 
+/* The same two calls for frames of uint16 samples (upstream RealESRGANer.enhance's 16-bit branch: img / 65535 in,
+ * round(clamp(out, 0, 1) * 65535) out).  [N][H][W][3] uint16 BGR -> [N][sH][sW][3] uint16 BGR. */
+int b200sr_enqueue_u16(b200sr_engine* e, const uint16_t* src_dev, uint16_t* dst_dev, int n, int h, int w, int tile,
+                       int tile_pad, int pre_pad, void* cuda_stream);
+int b200sr_upscale_host_u16(b200sr_engine* e, const uint16_t* src_host, uint16_t* dst_host, int n, int h, int w,
+                            int tile, int tile_pad, int pre_pad);
+
 /* Number of kernels the last enqueue launched (bench.py reports it as gpu_launches). */
 int b200sr_last_launch_count(const b200sr_engine* e);
 

@@ -26,7 +26,7 @@ NVCC_FLAGS = [
 EXPORTED_SYMBOLS = [
     "b200sr_create", "b200sr_destroy", "b200sr_num_convs", "b200sr_num_prelus", "b200sr_set_conv",
     "b200sr_set_prelu", "b200sr_finalize", "b200sr_output_dims", "b200sr_workspace_bytes",
-    "b200sr_enqueue_u8", "b200sr_upscale_host_u8", "b200sr_last_launch_count", "b200sr_set_option",
+    "b200sr_enqueue_u8", "b200sr_upscale_host_u8", "b200sr_enqueue_u16", "b200sr_upscale_host_u16", "b200sr_last_launch_count", "b200sr_set_option",
     "b200sr_last_error", "b200sr_version", "b200sr_debug_conv3x3", "b200sr_get_profile",
     "b200sr_debug_plan_regions", "b200sr_debug_pack_weights", "b200sr_debug_choose_th", "b200sr_debug_rdb_items", "b200sr_debug_rdb_flag_rows", "b200sr_debug_rdb_stats", "b200sr_debug_rdb_trace",
 ]
@@ -126,6 +126,10 @@ def load() -> ctypes.CDLL:
         lib.b200sr_enqueue_u8.restype = c_int
         lib.b200sr_upscale_host_u8.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int]
         lib.b200sr_upscale_host_u8.restype = c_int
+        lib.b200sr_enqueue_u16.argtypes = lib.b200sr_enqueue_u8.argtypes
+        lib.b200sr_enqueue_u16.restype = c_int
+        lib.b200sr_upscale_host_u16.argtypes = lib.b200sr_upscale_host_u8.argtypes
+        lib.b200sr_upscale_host_u16.restype = c_int
         lib.b200sr_last_launch_count.argtypes = [c_void_p]
         lib.b200sr_last_launch_count.restype = c_int
         lib.b200sr_set_option.argtypes = [c_void_p, c_char_p, c_int]

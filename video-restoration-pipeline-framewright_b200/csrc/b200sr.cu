@@ -307,6 +307,7 @@ struct Region {
   // source frame + padding
   const uint8_t* src;
   uint8_t* dst;
+  int sample16 = 0;            // frames hold uint16 samples (upstream's 16-bit image branch) instead of uint8
   int n, Hs, Ws, pre_pad, H1, W1;
   int oy, ox, rh, rw;          // region in padded-image coordinates
   int crop_y0, crop_x0, crop_h, crop_w, dst_y0, dst_x0, dst_h, dst_w;  // in network-output pixels
@@ -518,6 +519,7 @@ int run_first(b200sr_engine* e, const Region& R, int s, int H, int W, __nv_bfloa
   const Layer& l = e->layers[0];
   FirstArgs a{};
   a.src = R.src;
+  a.src16 = R.sample16;
   a.N = R.n;
   a.Hs = R.Hs;
   a.Ws = R.Ws;
@@ -632,6 +634,7 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
   ConvArgs base{};
   base.slope = 1.f;
   base.dst = R.dst;
+  base.dst16 = R.sample16;
   base.dst_h = R.dst_h;
   base.dst_w = R.dst_w;
   base.crop_y0 = R.crop_y0;
@@ -941,8 +944,10 @@ int b200sr_workspace_bytes(b200sr_engine* e, int n, int h, int w, int tile, int 
   return B200SR_OK;
 }
 
-int b200sr_enqueue_u8(b200sr_engine* e, const uint8_t* src_dev, uint8_t* dst_dev, int n, int h, int w, int tile,
-                      int tile_pad, int pre_pad, void* cuda_stream) {
+static int enqueue_impl(b200sr_engine* e, const void* src_dev_v, void* dst_dev_v, int n, int h, int w, int tile,
+                        int tile_pad, int pre_pad, void* cuda_stream, int sample16) {
+  const uint8_t* src_dev = static_cast<const uint8_t*>(src_dev_v);
+  uint8_t* dst_dev = static_cast<uint8_t*>(dst_dev_v);
   if (!e) return B200SR_ERR_INVALID;
   if (!e->finalized) return fail(e, B200SR_ERR_STATE, "weights not finalised");
   if (!src_dev || !dst_dev || n <= 0 || h <= 0 || w <= 0 || tile < 0 || tile_pad < 0 || pre_pad < 0)
@@ -961,6 +966,7 @@ int b200sr_enqueue_u8(b200sr_engine* e, const uint8_t* src_dev, uint8_t* dst_dev
   for (Region R : regions) {
     R.src = src_dev;
     R.dst = dst_dev;
+    R.sample16 = sample16;
     R.n = n;
     int rc = run_region(e, R, st);
     if (rc) return rc;
@@ -968,12 +974,22 @@ int b200sr_enqueue_u8(b200sr_engine* e, const uint8_t* src_dev, uint8_t* dst_dev
   return B200SR_OK;
 }
 
-int b200sr_upscale_host_u8(b200sr_engine* e, const uint8_t* src_host, uint8_t* dst_host, int n, int h, int w, int tile,
-                           int tile_pad, int pre_pad) {
+int b200sr_enqueue_u8(b200sr_engine* e, const uint8_t* src_dev, uint8_t* dst_dev, int n, int h, int w, int tile,
+                      int tile_pad, int pre_pad, void* cuda_stream) {
+  return enqueue_impl(e, src_dev, dst_dev, n, h, w, tile, tile_pad, pre_pad, cuda_stream, 0);
+}
+
+int b200sr_enqueue_u16(b200sr_engine* e, const uint16_t* src_dev, uint16_t* dst_dev, int n, int h, int w, int tile,
+                       int tile_pad, int pre_pad, void* cuda_stream) {
+  return enqueue_impl(e, src_dev, dst_dev, n, h, w, tile, tile_pad, pre_pad, cuda_stream, 1);
+}
+
+static int upscale_host_impl(b200sr_engine* e, const void* src_host, void* dst_host, int n, int h, int w, int tile,
+                             int tile_pad, int pre_pad, int sample16) {
   if (!e || !src_host || !dst_host || n <= 0 || h <= 0 || w <= 0) return B200SR_ERR_INVALID;
   CUDA_TRY(e, cudaSetDevice(e->device));
   if (!e->own_stream) CUDA_TRY(e, cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
-  const size_t in_bytes = static_cast<size_t>(n) * h * w * 3;
+  const size_t in_bytes = static_cast<size_t>(n) * h * w * 3 * (sample16 ? 2 : 1);
   const size_t out_bytes = in_bytes * e->desc.scale * e->desc.scale;
   if (in_bytes > e->stage_in_bytes) {
     if (e->stage_in) cudaFree(e->stage_in);
@@ -990,11 +1006,21 @@ int b200sr_upscale_host_u8(b200sr_engine* e, const uint8_t* src_host, uint8_t* d
     e->stage_out_bytes = out_bytes;
   }
   CUDA_TRY(e, cudaMemcpyAsync(e->stage_in, src_host, in_bytes, cudaMemcpyHostToDevice, e->own_stream));
-  int rc = b200sr_enqueue_u8(e, e->stage_in, e->stage_out, n, h, w, tile, tile_pad, pre_pad, e->own_stream);
+  int rc = enqueue_impl(e, e->stage_in, e->stage_out, n, h, w, tile, tile_pad, pre_pad, e->own_stream, sample16);
   if (rc) return rc;
   CUDA_TRY(e, cudaMemcpyAsync(dst_host, e->stage_out, out_bytes, cudaMemcpyDeviceToHost, e->own_stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->own_stream));
   return B200SR_OK;
+}
+
+int b200sr_upscale_host_u8(b200sr_engine* e, const uint8_t* src_host, uint8_t* dst_host, int n, int h, int w, int tile,
+                           int tile_pad, int pre_pad) {
+  return upscale_host_impl(e, src_host, dst_host, n, h, w, tile, tile_pad, pre_pad, 0);
+}
+
+int b200sr_upscale_host_u16(b200sr_engine* e, const uint16_t* src_host, uint16_t* dst_host, int n, int h, int w,
+                            int tile, int tile_pad, int pre_pad) {
+  return upscale_host_impl(e, src_host, dst_host, n, h, w, tile, tile_pad, pre_pad, 1);
 }
 
 int b200sr_last_launch_count(const b200sr_engine* e) { return e ? e->launches : 0; }

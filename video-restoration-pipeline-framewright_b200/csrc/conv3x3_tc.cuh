@@ -72,7 +72,8 @@ struct ConvArgs {
   const __nv_bfloat16* xb_hi;   // RRDB input x0.hi (EPI_RDB5_RRDB; may alias `out`)
   const uint8_t* xb_lo;         // RRDB input x0.lo
   const float* fadd;      // fp32 addend (EPI_ADD_F32) / normalised network input RGBx (EPI_SRVGG_LAST)
-  uint8_t* dst;           // u8 BGR destination frame(s)  [N][dst_h][dst_w][3]
+  uint8_t* dst;           // BGR destination frame(s)  [N][dst_h][dst_w][3], uint8 or (dst16) uint16 samples
+  int dst16;              // 16-bit output samples: round(clamp(v, 0, 1) * 65535)  (upstream's max_range = 65535 branch)
   int dst_h, dst_w;       // destination frame size
   int crop_y0, crop_x0;   // first conv-output pixel kept
   int crop_h, crop_w;     // kept extent
@@ -213,6 +214,12 @@ __device__ __forceinline__ uint8_t quant_u8(float v) {
   v = fminf(fmaxf(v, 0.f), 1.f);
   return static_cast<uint8_t>(__float2int_rn(v * 255.0f));
 }
+__device__ __forceinline__ uint16_t quant_u16(float v) {
+  v = fminf(fmaxf(v, 0.f), 1.f);
+  return static_cast<uint16_t>(__float2int_rn(v * 65535.0f));
+}
+// one output sample (channel ch of the BGR pixel at element index `px3`), 8- or 16-bit
+__device__ __forceinline__ void store_sample(const ConvArgs& a, size_t px3, int ch, float v);
 
 // Load this thread's COUT accumulator columns of one tile row.
 template <int COUT>
@@ -334,6 +341,13 @@ __device__ __forceinline__ void load_trunk_pair(const __nv_bfloat16* hi_px, cons
   for (int g = 0; g < 2; ++g) ld_global_256_ef(lo_px + g * LO_GSTRIDE, lo[g]);
 }
 
+__device__ __forceinline__ void store_sample(const ConvArgs& a, size_t px3, int ch, float v) {
+  if (a.dst16)
+    reinterpret_cast<uint16_t*>(a.dst)[px3 + ch] = quant_u16(v);
+  else
+    a.dst[px3 + ch] = quant_u8(v);
+}
+
 // Fused pointwise tail of one output pixel (one thread).
 template <int COUT, int EPI>
 __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* s_bias, const float* s_prelu,
@@ -379,10 +393,10 @@ __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* s
   } else if constexpr (EPI == EPI_LAST_U8) {
     const int cy = y - a.crop_y0, cx = x - a.crop_x0;
     if (cy >= 0 && cy < a.crop_h && cx >= 0 && cx < a.crop_w) {
-      uint8_t* d = a.dst + ((static_cast<size_t>(n) * a.dst_h + (a.dst_y0 + cy)) * a.dst_w + (a.dst_x0 + cx)) * 3;
-      d[0] = quant_u8(acc[2] + s_bias[2]);  // B
-      d[1] = quant_u8(acc[1] + s_bias[1]);  // G
-      d[2] = quant_u8(acc[0] + s_bias[0]);  // R
+      const size_t d = ((static_cast<size_t>(n) * a.dst_h + (a.dst_y0 + cy)) * a.dst_w + (a.dst_x0 + cx)) * 3;
+      store_sample(a, d, 0, acc[2] + s_bias[2]);  // B
+      store_sample(a, d, 1, acc[1] + s_bias[1]);  // G
+      store_sample(a, d, 2, acc[0] + s_bias[0]);  // R
     }
   } else {
     static_assert(EPI == EPI_SRVGG_LAST && COUT == 48, "SRVGG tail needs 48 channels");
@@ -396,11 +410,11 @@ __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* s
       for (int j = 0; j < 4; ++j) {
         const int cx = x * 4 + j - a.crop_x0;
         if (cx < 0 || cx >= a.crop_w) continue;
-        uint8_t* d = a.dst + ((static_cast<size_t>(n) * a.dst_h + (a.dst_y0 + cy)) * a.dst_w + (a.dst_x0 + cx)) * 3;
+        const size_t d = ((static_cast<size_t>(n) * a.dst_h + (a.dst_y0 + cy)) * a.dst_w + (a.dst_x0 + cx)) * 3;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const int o = c * 16 + i * 4 + j;
-          d[2 - c] = quant_u8(acc[o] + s_bias[o] + base[c]);
+          store_sample(a, d, 2 - c, acc[o] + s_bias[o] + base[c]);
         }
       }
     }

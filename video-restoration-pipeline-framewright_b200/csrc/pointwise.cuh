@@ -11,6 +11,7 @@ namespace b200sr {
 
 struct FirstArgs {
   const uint8_t* src;   // [N][Hs][Ws][3] u8 BGR
+  int src16;            // samples are uint16 (normalised by 65535) instead of uint8 (by 255)
   int N, Hs, Ws;
   int H1, W1;           // Hs + pre_pad, Ws + pre_pad
   int oy, ox;           // origin of this region in the padded image
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(128) first_conv_kernel(const FirstArgs a) {
   float acc[64];
 #pragma unroll
   for (int c = 0; c < 64; ++c) acc[c] = s_b[c];
-  const uint8_t* img = a.src + static_cast<size_t>(n) * a.Hs * a.Ws * 3;
+  const size_t img = static_cast<size_t>(n) * a.Hs * a.Ws * 3;   // first sample of frame n
   float centre[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
   for (int tap = 0; tap < 9; ++tap) {
@@ -66,9 +67,11 @@ __global__ void __launch_bounds__(128) first_conv_kernel(const FirstArgs a) {
       for (int dx = 0; dx < S; ++dx) {
         const int sy = reflect_src(a.oy + yy * S + dy, a.Hs, a.H1);
         const int sx = reflect_src(a.ox + xx * S + dx, a.Ws, a.W1);
-        const uint8_t* p = img + (static_cast<size_t>(sy) * a.Ws + sx) * 3;
+        const size_t p = img + (static_cast<size_t>(sy) * a.Ws + sx) * 3;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) in[c * S * S + dy * S + dx] = static_cast<float>(p[2 - c]) / 255.0f;  // BGR->RGB
+        for (int c = 0; c < 3; ++c)   // BGR -> RGB, img / max_range as upstream's pre_process
+          in[c * S * S + dy * S + dx] = a.src16 ? static_cast<float>(reinterpret_cast<const uint16_t*>(a.src)[p + 2 - c]) / 65535.0f
+                                                : static_cast<float>(a.src[p + 2 - c]) / 255.0f;
       }
     if (S == 1 && tap == 4) {
       centre[0] = in[0];

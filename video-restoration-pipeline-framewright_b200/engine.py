@@ -97,39 +97,43 @@ class B200Engine:
 
     def upscale_device(self, frames: torch.Tensor, out: Optional[torch.Tensor] = None, tile: int = 0,
                        tile_pad: int = 10, pre_pad: int = 0) -> torch.Tensor:
-        """frames: CUDA uint8 [N,H,W,3] BGR (contiguous) -> CUDA uint8 [N,H*s,W*s,3]; async on the current stream."""
-        if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3 or not frames.is_cuda:
-            raise EngineError("frames must be a CUDA uint8 tensor [N,H,W,3]")
+        """frames: CUDA uint8 (or uint16: upstream's 16-bit image branch) [N,H,W,3] BGR (contiguous) -> CUDA tensor of
+        the same dtype [N,H*s,W*s,3]; async on the current stream."""
+        if frames.dtype not in (torch.uint8, torch.uint16) or frames.dim() != 4 or frames.shape[-1] != 3 or not frames.is_cuda:
+            raise EngineError("frames must be a CUDA uint8 / uint16 tensor [N,H,W,3]")
         if frames.device.index != self.gpu_id:
             raise EngineError(f"frames live on cuda:{frames.device.index}, engine on cuda:{self.gpu_id}")
         frames = frames.contiguous()
         n, h, w, _ = frames.shape
         s = self.scale
         if out is None:
-            out = torch.empty((n, h * s, w * s, 3), dtype=torch.uint8, device=frames.device)
-        elif tuple(out.shape) != (n, h * s, w * s, 3) or out.dtype != torch.uint8 or not out.is_contiguous():
+            out = torch.empty((n, h * s, w * s, 3), dtype=frames.dtype, device=frames.device)
+        elif tuple(out.shape) != (n, h * s, w * s, 3) or out.dtype != frames.dtype or not out.is_contiguous():
             raise EngineError("bad output tensor")
         stream = torch.cuda.current_stream(frames.device).cuda_stream
-        rc = self._lib.b200sr_enqueue_u8(self._h, frames.data_ptr(), out.data_ptr(), n, h, w, int(tile), int(tile_pad),
-                                         int(pre_pad), ctypes.c_void_p(stream))
+        fn = self._lib.b200sr_enqueue_u16 if frames.dtype == torch.uint16 else self._lib.b200sr_enqueue_u8
+        rc = fn(self._h, frames.data_ptr(), out.data_ptr(), n, h, w, int(tile), int(tile_pad), int(pre_pad),
+                ctypes.c_void_p(stream))
         self._check(rc, "enqueue_u8")
         return out
 
     def upscale_host(self, frames: np.ndarray, out: Optional[np.ndarray] = None, tile: int = 0, tile_pad: int = 10,
                      pre_pad: int = 0) -> np.ndarray:
-        """frames: host uint8 [N,H,W,3] or [H,W,3] BGR -> host uint8, through the C ABI's host-buffer call
-        (H2D + forward + D2H + sync inside)."""
+        """frames: host uint8 (or uint16) [N,H,W,3] or [H,W,3] BGR -> host array of the same dtype, through the C ABI's
+        host-buffer call (H2D + forward + D2H + sync inside)."""
         single = frames.ndim == 3
         f = np.ascontiguousarray(frames[None] if single else frames)
-        if f.dtype != np.uint8 or f.ndim != 4 or f.shape[-1] != 3:
-            raise EngineError("frames must be uint8 [N,H,W,3] or [H,W,3]")
+        if f.dtype not in (np.uint8, np.uint16) or f.ndim != 4 or f.shape[-1] != 3:
+            raise EngineError("frames must be uint8 / uint16 [N,H,W,3] or [H,W,3]")
         n, h, w, _ = f.shape
         s = self.scale
         if out is None:
-            out = np.empty((n, h * s, w * s, 3), dtype=np.uint8)
-        rc = self._lib.b200sr_upscale_host_u8(self._h, f.ctypes.data_as(ctypes.c_void_p),
-                                              out.ctypes.data_as(ctypes.c_void_p), n, h, w, int(tile), int(tile_pad),
-                                              int(pre_pad))
+            out = np.empty((n, h * s, w * s, 3), dtype=f.dtype)
+        elif out.dtype != f.dtype or tuple(out.shape) != (n, h * s, w * s, 3) or not out.flags["C_CONTIGUOUS"]:
+            raise EngineError("bad output array")
+        fn = self._lib.b200sr_upscale_host_u16 if f.dtype == np.uint16 else self._lib.b200sr_upscale_host_u8
+        rc = fn(self._h, f.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), n, h, w, int(tile),
+                int(tile_pad), int(pre_pad))
         self._check(rc, "upscale_host_u8")
         return out[0] if single else out
 

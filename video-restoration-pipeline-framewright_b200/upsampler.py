@@ -121,23 +121,24 @@ class RealESRGANer:
         self._lock = threading.Lock()
 
     # --------------------------------------------------------------------------------------------
-    def _run_u8(self, img_bgr_u8: np.ndarray) -> np.ndarray:
+    def _run_u8(self, img_bgr_u8: np.ndarray) -> np.ndarray:   # uint8 or uint16 samples
         with self._lock:
             return self._engine.upscale_host(img_bgr_u8, tile=self.tile_size, tile_pad=self.tile_pad,
                                              pre_pad=self.pre_pad)
 
     def enhance(self, img: np.ndarray, outscale: Optional[float] = None,
                 alpha_upsampler: str = "realesrgan") -> Tuple[np.ndarray, str]:
-        """uint8 BGR / gray / BGRA ndarray -> (uint8 ndarray scaled by `outscale` or the net scale, img_mode)."""
+        """BGR / gray / BGRA ndarray -> (ndarray scaled by `outscale` or the net scale, img_mode).  uint8 in ->
+        uint8 out; an image whose maximum exceeds 256 is a 16-bit image as upstream (`max_range = 65535`): it runs
+        through the engine's uint16 path and comes back as uint16."""
         import cv2
 
         if not isinstance(img, np.ndarray) or img.ndim not in (2, 3):
             raise EngineError("img must be an HxW or HxWxC ndarray")
         h_input, w_input = img.shape[0:2]
         if img.dtype != np.uint8:
-            if np.max(img) > 256:
-                raise NotImplementedError("16-bit input is not supported by the B200 uint8 engine path")
-            img = img.astype(np.uint8)
+            # upstream: img.astype(float32); max_range = 65535 if np.max(img) > 256 else 255
+            img = img.astype(np.uint16) if np.max(img) > 256 else img.astype(np.uint8)
         if img.ndim == 2:
             img_mode = "L"
             out = self._run_u8(cv2.cvtColor(img, cv2.COLOR_GRAY2BGR))
