@@ -242,3 +242,19 @@ def test_distributor_process_fn_retry_on_other_gpu(tmp_path):
     assert res.total_frames == 6 and not res.errors
     assert ("f2.png", 0) in seen and ("f2.png", 1) in seen and frames[2] in res.retried_frames
     assert res.speedup_factor > 1.0
+
+
+def test_dni_interpolates_state_dicts():
+    """RealESRGANer.dni (upstream: blend of two checkpoints by dni_weight), on plain and file-style wrapped dicts."""
+    import torch
+
+    from framewright_b200.upsampler import RealESRGANer
+
+    a = {"w": torch.ones(2, 3), "b": torch.zeros(3)}
+    b = {"w": torch.full((2, 3), 3.0), "b": torch.ones(3)}
+    out = RealESRGANer.dni(a, {"params": b}, [0.25, 0.75])
+    assert torch.allclose(out["w"], torch.full((2, 3), 2.5)) and torch.allclose(out["b"], torch.full((3,), 0.75))
+    import pytest
+    from framewright_b200.engine import EngineError
+    with pytest.raises(EngineError):
+        RealESRGANer.dni(a, {"w": torch.ones(2, 3)}, [0.5, 0.5])

@@ -81,8 +81,20 @@ class RealESRGANer:
         self.pre_pad = int(pre_pad)
         self.mod_scale = None
         self.half = bool(half)  # accepted for API parity; the engine always computes bf16-in / fp32-accumulate
+        # upstream: `dni_weight` blends two checkpoints of one architecture (realesr-general-x4v3 + its -wdn twin for
+        # the denoise strength): model_path is then a list of two paths.  Also accepted: state_dict=[sd_a, sd_b].
+        dni_pair = None
         if dni_weight is not None:
-            raise NotImplementedError("dni_weight (network interpolation) is not supported by the B200 engine")
+            if len(dni_weight) != 2:
+                raise EngineError("dni_weight must hold two weights")
+            if isinstance(state_dict, (list, tuple)) and len(state_dict) == 2:
+                dni_pair = (state_dict[0], state_dict[1])
+                state_dict = None
+            elif isinstance(model_path, (list, tuple)) and len(model_path) == 2:
+                dni_pair = tuple(_load_checkpoint(str(p)) for p in model_path)
+            else:
+                raise EngineError("dni_weight needs two checkpoints: model_path=[a, b] (local files) or state_dict=[a, b]")
+            model_path = model_path[0] if isinstance(model_path, (list, tuple)) else model_path
         if gpu_id is None:
             gpu_id = device.index if isinstance(device, torch.device) and device.index is not None else 0
         self.gpu_id = int(gpu_id)
@@ -105,6 +117,8 @@ class RealESRGANer:
         if arch.scale != self.scale:
             raise EngineError(f"scale {self.scale} does not match the {arch.kind} network scale {arch.scale}")
 
+        if dni_pair is not None:
+            state_dict = self.dni(dni_pair[0], dni_pair[1], dni_weight)
         if state_dict is None:
             local = str(model_path) if model_path and os.path.isfile(str(model_path)) else None
             if local is not None:
@@ -119,6 +133,21 @@ class RealESRGANer:
         self.arch = arch
         self._engine = B200Engine(arch, state_dict, gpu_id=self.gpu_id)
         self._lock = threading.Lock()
+
+    @staticmethod
+    def dni(net_a: Dict[str, torch.Tensor], net_b: Dict[str, torch.Tensor], dni_weight, key: str = "params",
+            loc: str = "cpu") -> Dict[str, torch.Tensor]:
+        """Deep network interpolation (upstream RealESRGANer.dni): w = dni_weight[0] * a + dni_weight[1] * b per
+        tensor.  Takes state dicts (optionally wrapped as {"params": ...} / {"params_ema": ...} like the files)."""
+        def unwrap(sd):
+            for k in ("params_ema", key):
+                if isinstance(sd, dict) and k in sd and isinstance(sd[k], dict):
+                    return sd[k]
+            return sd
+        a, b = unwrap(net_a), unwrap(net_b)
+        if set(a.keys()) != set(b.keys()):
+            raise EngineError("dni: the two checkpoints have different tensors")
+        return {k: float(dni_weight[0]) * a[k].float() + float(dni_weight[1]) * b[k].float() for k in a}
 
     # --------------------------------------------------------------------------------------------
     def _run_u8(self, img_bgr_u8: np.ndarray) -> np.ndarray:   # uint8 or uint16 samples
