@@ -22,6 +22,8 @@ def run(N, offs, reps=2, inter=0):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     print(f"N={N} off={offs} interleave={inter}: {ms:8.2f} ms/step  {N/ms*1e3:6.2f} frames/s", flush=True)
-for N in (4, 6, 8, 12, 4, 8):
-    run(N, (1,2,3,5), inter=-1)
+for order in (1234, 40123, 43210, 4123, 1234, 40123):   # digits = conv order within a step (leading 0 dropped)
+    eng.set_option("rdb_order", order)
+    print("order", f"{order:05d}", end=" ")
+    run(4, (1,2,3,5), inter=-1)
 eng.close()
