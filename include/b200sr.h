@@ -8,8 +8,12 @@
  * binds these with ctypes; INTEGRATION.md shows the stub.
  *
  * Conventions: plain C, no exceptions, no torch types.  Every function returns a status
- * code (B200SR_OK == 0); b200sr_last_error() gives the message.  One engine per (GPU,
- * stream); an engine is not thread-safe (callers serialise or use one engine per thread).
+ * code (B200SR_OK == 0); b200sr_last_error() gives the message of the calling thread's last
+ * failed call.  One engine per GPU.  Threading: the host-buffer calls (b200sr_upscale_host_*)
+ * are thread-safe -- each takes one of the engine's lanes (stream + workspace + staging), which is
+ * how the reference's parallel_frames threads (restorer.py:1894) overlap copies and kernels; the
+ * device-pointer calls (b200sr_enqueue_*) are stream-ordered and must be ordered with each other
+ * by the caller; weight loading / options / destroy need the engine idle.
  * Frames are uint8 HWC, BGR channel order (what cv2.imread yields, pytorch_realesrgan.py:198).
  */
 #ifndef B200SR_H_
@@ -76,7 +80,12 @@ int b200sr_workspace_bytes(b200sr_engine* e, int n, int h, int w, int tile, int 
 int b200sr_enqueue_u8(b200sr_engine* e, const uint8_t* src_dev, uint8_t* dst_dev, int n, int h, int w, int tile,
                       int tile_pad, int pre_pad, void* cuda_stream);
 
-/* Same with HOST buffers: H2D copy, run, D2H copy, stream sync (the end-to-end call). */
+/* Same with HOST buffers (the end-to-end call, what RealESRGANer.enhance's `.to(device)` ... `.cpu()` does,
+ * called at processors/pytorch_realesrgan.py:223): the n frames are cut into jobs of a few frames, each job
+ * queues H2D copy -> forward -> D2H copy on a free lane's stream, two lanes by default, so uploads and
+ * downloads overlap the neighbouring job's kernels (and those of concurrent callers).  Pinned buffers
+ * (b200sr_host_alloc / b200sr_host_register) are copied directly, pageable ones staged through pinned memory.
+ * Returns when dst_host holds the result.  Thread-safe. */
 int b200sr_upscale_host_u8(b200sr_engine* e, const uint8_t* src_host, uint8_t* dst_host, int n, int h, int w,
                            int tile, int tile_pad, int pre_pad);
 
@@ -87,6 +96,13 @@ int b200sr_enqueue_u16(b200sr_engine* e, const uint16_t* src_dev, uint16_t* dst_
 int b200sr_upscale_host_u16(b200sr_engine* e, const uint16_t* src_host, uint16_t* dst_host, int n, int h, int w,
                             int tile, int tile_pad, int pre_pad);
 
+/* Pinned host memory: allocate (cudaHostAlloc, portable) / free, or pin an existing range (shared-memory frame
+ * rings of the multi-GPU scheduler) so that the host-buffer calls copy without staging. */
+void* b200sr_host_alloc(size_t bytes);
+void b200sr_host_free(void* p);
+int b200sr_host_register(void* p, size_t bytes);
+int b200sr_host_unregister(void* p);
+
 /* Number of kernels the last enqueue launched (bench.py reports it as gpu_launches). */
 int b200sr_last_launch_count(const b200sr_engine* e);
 
@@ -94,6 +110,8 @@ int b200sr_last_launch_count(const b200sr_engine* e);
  * Options: "fused_rdb" (1: one persistent kernel per residual dense block; 0: five per-conv launches, same bytes),
  * "fold_up" (1: conv_up1/up2 read the nearest-2x upsampling through the duplicated-pixel TMA view; 0: materialise it),
  * "profile" (1: CUDA events around every launch, read with b200sr_get_profile), "force_th", "max_ctas",
+ * "lanes" (host-buffer lanes, default 2), "host_chunk" (frames per lane job, 0 = auto), "ws_limit_mb" (tests: refuse
+ * larger workspaces with B200SR_ERR_OOM),
  * "rdb_off" / "rdb_order" (fused work-list schedule), "rdb_stats" (instrumented builds only). */
 int b200sr_set_option(b200sr_engine* e, const char* key, int value);
 

@@ -63,6 +63,15 @@ def test_reference_processor_calls_shim(ref_modules, tmp_path, monkeypatch):
             pass
 
     monkeypatch.setattr(up_mod, "B200Engine", OracleEngine)
+    # the reference hands RealESRGANer the release URL of the checkpoint; offline, the shim resolves it to the file of
+    # that name in the weights directory (and raises if there is none -- never random weights)
+    import torch
+
+    wdir = tmp_path / "weights"
+    wdir.mkdir()
+    torch.save({"params_ema": make_synthetic_state_dict("RealESRGAN_x4plus_anime_6B", 0)},
+               str(wdir / "RealESRGAN_x4plus_anime_6B.pth"))
+    monkeypatch.setenv("B200SR_WEIGHTS_DIR", str(wdir))
     # the reference probes `import torch; from realesrgan import RealESRGANer; from basicsr... import RRDBNet`
     assert pr.is_pytorch_esrgan_available() is True
     img = oracle.synthetic_frame(24, 28, seed=2, kind="mixed")

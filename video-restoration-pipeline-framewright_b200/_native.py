@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = [
     "b200sr_create", "b200sr_destroy", "b200sr_num_convs", "b200sr_num_prelus", "b200sr_set_conv",
     "b200sr_set_prelu", "b200sr_finalize", "b200sr_output_dims", "b200sr_workspace_bytes",
     "b200sr_enqueue_u8", "b200sr_upscale_host_u8", "b200sr_enqueue_u16", "b200sr_upscale_host_u16", "b200sr_last_launch_count", "b200sr_set_option",
+    "b200sr_host_alloc", "b200sr_host_free", "b200sr_host_register", "b200sr_host_unregister",
     "b200sr_last_error", "b200sr_version", "b200sr_debug_conv3x3", "b200sr_get_profile",
     "b200sr_debug_plan_regions", "b200sr_debug_pack_weights", "b200sr_debug_choose_th", "b200sr_debug_rdb_items", "b200sr_debug_rdb_flag_rows", "b200sr_debug_rdb_stats", "b200sr_debug_rdb_trace",
 ]
@@ -130,6 +131,14 @@ def load() -> ctypes.CDLL:
         lib.b200sr_enqueue_u16.restype = c_int
         lib.b200sr_upscale_host_u16.argtypes = lib.b200sr_upscale_host_u8.argtypes
         lib.b200sr_upscale_host_u16.restype = c_int
+        lib.b200sr_host_alloc.argtypes = [ctypes.c_size_t]
+        lib.b200sr_host_alloc.restype = c_void_p
+        lib.b200sr_host_free.argtypes = [c_void_p]
+        lib.b200sr_host_free.restype = None
+        lib.b200sr_host_register.argtypes = [c_void_p, ctypes.c_size_t]
+        lib.b200sr_host_register.restype = c_int
+        lib.b200sr_host_unregister.argtypes = [c_void_p]
+        lib.b200sr_host_unregister.restype = c_int
         lib.b200sr_last_launch_count.argtypes = [c_void_p]
         lib.b200sr_last_launch_count.restype = c_int
         lib.b200sr_set_option.argtypes = [c_void_p, c_char_p, c_int]

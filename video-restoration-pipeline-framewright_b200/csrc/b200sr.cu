@@ -3,9 +3,14 @@
 // conv3x3_tc.cuh / pointwise.cuh, plus the RealESRGANer pre/post/tile logic
 // (reference call site: /root/reference/src/framewright/processors/pytorch_realesrgan.py:160-170, 223).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -58,6 +63,30 @@ inline uint16_t f2h(float f) {
 
 }  // namespace
 
+// One lane = everything a forward pass needs exclusively: a stream, the activation workspace, the fused-RDB
+// work list + completion counters, and (host-buffer calls) device + pinned staging.  Host-buffer calls take a free
+// lane each, so concurrent callers (the reference's parallel_frames threads, restorer.py:1894) and the chunks of one
+// large call overlap their H2D / D2H copies and launch tails with each other's kernels.
+struct Lane {
+  int id = 0;
+  bool busy = false;
+  cudaStream_t stream = nullptr;
+  uint8_t* ws = nullptr;          // workspace (grow-only)
+  size_t ws_bytes = 0;
+  // fused-RDB item table (depends only on N, H, W) and its counters
+  int rdb_n = 0, rdb_h = 0, rdb_w = 0, rdb_nitems = 0, rdb_nflags = 0, rdb_gen = -1;
+  RdbItem* d_rdb_items = nullptr;
+  int* d_rdb_flags = nullptr;
+  int rdb_launch_idx = 0;
+  int launches = 0;
+  // staging of the host-buffer entry point
+  uint8_t* dev_in = nullptr;
+  uint8_t* dev_out = nullptr;
+  uint8_t* pin_in = nullptr;
+  uint8_t* pin_out = nullptr;
+  size_t dev_in_bytes = 0, dev_out_bytes = 0, pin_in_bytes = 0, pin_out_bytes = 0;
+};
+
 struct b200sr_engine {
   b200sr_model_desc desc{};
   int device = 0;
@@ -67,30 +96,26 @@ struct b200sr_engine {
   std::vector<float*> prelu_dev;
   bool finalized = false;
   std::string err;
-  // workspace (grow-only)
-  uint8_t* ws = nullptr;
-  size_t ws_bytes = 0;
-  // staging for the host-buffer entry point
-  uint8_t* stage_in = nullptr;
-  uint8_t* stage_out = nullptr;
-  size_t stage_in_bytes = 0, stage_out_bytes = 0;
-  cudaStream_t own_stream = nullptr;
-  int launches = 0;
+  // lanes: `dev_lane` serves the device-pointer entry points (caller's stream), `lanes` the host-buffer ones
+  std::mutex mu;                   // lane acquisition, err, prof
+  std::condition_variable cv;
+  Lane dev_lane;
+  std::vector<std::unique_ptr<Lane>> lanes;
+  int opt_lanes = 2;
+  int opt_host_chunk = 0;          // frames per lane job of a host-buffer call (0 = auto)
+  long long opt_ws_limit_mb = 0;   // > 0: refuse workspaces above this size (tests: forces the OOM path)
+  std::atomic<int> last_launches{0};
   int opt_force_th = 0;     // 0 = auto
   int opt_max_ctas = 0;     // 0 = one per SM
-  bool attrs_set = false;
   // optional per-kernel-class timing (CUDA events around every launch; option "profile")
   int opt_fused_rdb = 1;    // run each RDB as one persistent kernel (L2-resident intermediates)
   int opt_fold_up = 1;      // conv_up1/up2 read the nearest-2x upsampling through the duplicated-pixel TMA view
   int opt_rdb_stats = 0;    // dev: collect per-CTA cycle counters of the k-th fused launch of a forward pass (1-based)
-  int rdb_launch_idx = 0;
+  int rdb_gen = 0;          // bumped when a schedule option changes: lanes rebuild their work lists
+  int stats_nitems = 0;
   long long* d_rdb_stats = nullptr;
   long long* d_rdb_trace = nullptr;
   long long* d_rdb_trace2 = nullptr;
-  // fused-RDB item table (depends only on N, H, W)
-  int rdb_n = 0, rdb_h = 0, rdb_w = 0, rdb_nitems = 0, rdb_nflags = 0;
-  RdbItem* d_rdb_items = nullptr;
-  int* d_rdb_flags = nullptr;
   int opt_profile = 0;
   struct ProfRec {
     int cls;
@@ -108,8 +133,14 @@ enum ProfClass {
 
 namespace {
 
+thread_local std::string tls_err;   // message of the last failed call on this thread (engines are shared by threads)
+
 int fail(b200sr_engine* e, int code, const std::string& msg) {
-  if (e) e->err = msg;
+  tls_err = msg;
+  if (e) {
+    std::lock_guard<std::mutex> g(e->mu);
+    e->err = msg;
+  }
   return code;
 }
 
@@ -130,13 +161,16 @@ struct ProfScope {
   bool on;
   ProfScope(b200sr_engine* e_, int cls, double flops, cudaStream_t st_) : e(e_), st(st_), on(e_->opt_profile != 0) {
     if (!on) return;
+    std::lock_guard<std::mutex> g(e->mu);
     b200sr_engine::ProfRec r{cls, flops, prof_event(e), prof_event(e)};
     cudaEventRecord(r.e0, st);
     idx = e->prof.size();
     e->prof.push_back(r);
   }
   ~ProfScope() {
-    if (on) cudaEventRecord(e->prof[idx].e1, st);
+    if (!on) return;
+    std::lock_guard<std::mutex> g(e->mu);
+    cudaEventRecord(e->prof[idx].e1, st);
   }
 };
 
@@ -144,6 +178,7 @@ struct ProfScope {
   do {                                                                                             \
     cudaError_t err__ = (expr);                                                                    \
     if (err__ != cudaSuccess) {                                                                    \
+      cudaGetLastError(); /* reset the sticky-until-read error so the next launch check is clean */ \
       int code__ = (err__ == cudaErrorMemoryAllocation) ? B200SR_ERR_OOM : B200SR_ERR_CUDA;        \
       return fail(e, code__, std::string(#expr) + ": " + cudaGetErrorString(err__));               \
     }                                                                                              \
@@ -222,8 +257,8 @@ std::vector<uint8_t> pack_weights(const Layer& l) {
 }
 
 template <int COUT, int EPI>
-int launch_conv_inst(b200sr_engine* e, const CUtensorMap& amap, const ConvArgs& a, cudaStream_t st, int pcls,
-                     double flops) {
+int launch_conv_inst(b200sr_engine* e, Lane* lane, const CUtensorMap& amap, const ConvArgs& a, cudaStream_t st,
+                     int pcls, double flops) {
   using Cfg = ConvCfg<COUT>;
   ProfScope prof_scope(e, pcls, flops, st);
   static bool attr_done[16] = {};
@@ -235,7 +270,7 @@ int launch_conv_inst(b200sr_engine* e, const CUtensorMap& amap, const ConvArgs& 
   int grid = std::min(a.ntiles, e->opt_max_ctas > 0 ? e->opt_max_ctas : e->num_sms * Cfg::CTAS_PER_SM);
   kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>>(amap, a);
   CUDA_TRY(e, cudaGetLastError());
-  e->launches++;
+  lane->launches++;
   return B200SR_OK;
 }
 
@@ -267,7 +302,7 @@ struct ConvIO {
   int up2 = 0;      // `in` is [N][H/2][W/2][pitch]; the conv reads its nearest-2x upsampling (ConvArgs::in_up2)
 };
 
-int launch_conv(b200sr_engine* e, const Layer& l, int epi, const ConvIO& io, ConvArgs a, cudaStream_t st) {
+int launch_conv(b200sr_engine* e, Lane* lane, const Layer& l, int epi, const ConvIO& io, ConvArgs a, cudaStream_t st) {
   CUtensorMap amap;
   const bool map_ok = io.up2 ? tmap_encode_act_up2(&amap, io.in, io.N, io.H / 2, io.W / 2, io.in_pitch, 64, 66, 128)
                              : tmap_encode_act(&amap, io.in, io.planes ? io.planes * io.N : io.N, io.H, io.W, io.in_pitch,
@@ -290,14 +325,14 @@ int launch_conv(b200sr_engine* e, const Layer& l, int epi, const ConvIO& io, Con
   // algorithmic FLOPs of this launch: true channel counts, every output pixel, 9 taps
   const double fl = 2.0 * 9.0 * l.cin * l.cout * static_cast<double>(io.N) * io.H * io.W;
   switch (l.coutp * 16 + epi) {
-    case 32 * 16 + EPI_ACT_BF16: return launch_conv_inst<32, EPI_ACT_BF16>(e, amap, a, st, PC_CONV32_ACT, fl);
-    case 64 * 16 + EPI_ACT_BF16: return launch_conv_inst<64, EPI_ACT_BF16>(e, amap, a, st, PC_CONV64_ACT, fl);
-    case 64 * 16 + EPI_PRELU_BF16: return launch_conv_inst<64, EPI_PRELU_BF16>(e, amap, a, st, PC_CONV64_PRELU, fl);
-    case 64 * 16 + EPI_RDB5: return launch_conv_inst<64, EPI_RDB5>(e, amap, a, st, PC_CONV64_RDB5, fl);
-    case 64 * 16 + EPI_RDB5_RRDB: return launch_conv_inst<64, EPI_RDB5_RRDB>(e, amap, a, st, PC_CONV64_RDB5_RRDB, fl);
-    case 64 * 16 + EPI_ADD_F32: return launch_conv_inst<64, EPI_ADD_F32>(e, amap, a, st, PC_CONV64_ADD, fl);
-    case 16 * 16 + EPI_LAST_U8: return launch_conv_inst<16, EPI_LAST_U8>(e, amap, a, st, PC_CONV16_LAST, fl);
-    case 48 * 16 + EPI_SRVGG_LAST: return launch_conv_inst<48, EPI_SRVGG_LAST>(e, amap, a, st, PC_CONV48_SRVGG_LAST, fl);
+    case 32 * 16 + EPI_ACT_BF16: return launch_conv_inst<32, EPI_ACT_BF16>(e, lane, amap, a, st, PC_CONV32_ACT, fl);
+    case 64 * 16 + EPI_ACT_BF16: return launch_conv_inst<64, EPI_ACT_BF16>(e, lane, amap, a, st, PC_CONV64_ACT, fl);
+    case 64 * 16 + EPI_PRELU_BF16: return launch_conv_inst<64, EPI_PRELU_BF16>(e, lane, amap, a, st, PC_CONV64_PRELU, fl);
+    case 64 * 16 + EPI_RDB5: return launch_conv_inst<64, EPI_RDB5>(e, lane, amap, a, st, PC_CONV64_RDB5, fl);
+    case 64 * 16 + EPI_RDB5_RRDB: return launch_conv_inst<64, EPI_RDB5_RRDB>(e, lane, amap, a, st, PC_CONV64_RDB5_RRDB, fl);
+    case 64 * 16 + EPI_ADD_F32: return launch_conv_inst<64, EPI_ADD_F32>(e, lane, amap, a, st, PC_CONV64_ADD, fl);
+    case 16 * 16 + EPI_LAST_U8: return launch_conv_inst<16, EPI_LAST_U8>(e, lane, amap, a, st, PC_CONV16_LAST, fl);
+    case 48 * 16 + EPI_SRVGG_LAST: return launch_conv_inst<48, EPI_SRVGG_LAST>(e, lane, amap, a, st, PC_CONV48_SRVGG_LAST, fl);
     default: return fail(e, B200SR_ERR_INVALID, "no kernel instance for this (Cout, epilogue)");
   }
 }
@@ -313,9 +348,19 @@ struct Region {
   int crop_y0, crop_x0, crop_h, crop_w, dst_y0, dst_x0, dst_h, dst_w;  // in network-output pixels
 };
 
+// The HR tail (conv_up1 .. conv_last) runs in groups of `tail_group` frames so that its 2x / 4x tensors (75 % of the
+// activation bytes) are sized for ~one 720p frame instead of the whole batch; frames are independent, so the bytes
+// produced do not depend on the grouping.
+int tail_group(int N, int H, int W) {
+  const long budget = 1280L * 720L;
+  const long px = static_cast<long>(H) * W;
+  return static_cast<int>(std::max(1L, std::min(static_cast<long>(N), budget / std::max(px, 1L))));
+}
+
 size_t region_ws_bytes(const b200sr_engine* e, int N, int H, int W) {
   const size_t px = static_cast<size_t>(N) * H * W;
   const size_t pxt = static_cast<size_t>(N) * H * ((W + 127) / 128) * 128;   // fp32 trunk: width padded to 128
+  const size_t tpx = static_cast<size_t>(tail_group(N, H, W)) * H * W;
   size_t total = 0;
   auto add = [&](size_t b) { total += align_up(b, 1024); };
   if (e->desc.arch == B200SR_ARCH_RRDB) {
@@ -326,10 +371,10 @@ size_t region_ws_bytes(const b200sr_engine* e, int N, int H, int W) {
     add(pxt * 64);                // residual-stream lo bytes A, B
     add(pxt * 64 * 4);            // f0 (tile-interleaved fp32)
     add(px * 64 * 2);             // conv_body out
-    add(px * 4 * 64 * 2);
-    add(px * 4 * 64 * 2);         // 2x: upsampled, conv_up1 out
-    add(px * 16 * 64 * 2);
-    add(px * 16 * 64 * 2);        // 4x ping-pong
+    add(tpx * 4 * 64 * 2);
+    add(tpx * 4 * 64 * 2);        // 2x: upsampled (fold_up = 0 only), conv_up1 out
+    add(tpx * 16 * 64 * 2);
+    add(tpx * 16 * 64 * 2);       // 4x ping-pong
   } else {
     add(px * 64 * 2);
     add(px * 64 * 2);
@@ -338,14 +383,17 @@ size_t region_ws_bytes(const b200sr_engine* e, int N, int H, int W) {
   return total;
 }
 
-int ensure_ws(b200sr_engine* e, size_t bytes, cudaStream_t st) {
-  if (bytes <= e->ws_bytes) return B200SR_OK;
-  if (e->ws) {
+int ensure_ws(b200sr_engine* e, Lane* lane, size_t bytes, cudaStream_t st) {
+  if (bytes <= lane->ws_bytes) return B200SR_OK;
+  if (e->opt_ws_limit_mb > 0 && bytes > (static_cast<size_t>(e->opt_ws_limit_mb) << 20))
+    return fail(e, B200SR_ERR_OOM, std::string("out of memory: ") + std::to_string(bytes >> 20) +
+                                       " MiB workspace exceeds the configured limit (option ws_limit_mb)");
+  if (lane->ws) {
     CUDA_TRY(e, cudaStreamSynchronize(st));
-    CUDA_TRY(e, cudaDeviceSynchronize());
-    cudaFree(e->ws);
-    e->ws = nullptr;
-    e->ws_bytes = 0;
+    if (lane == &e->dev_lane) CUDA_TRY(e, cudaDeviceSynchronize());   // earlier enqueues may sit on other streams
+    cudaFree(lane->ws);
+    lane->ws = nullptr;
+    lane->ws_bytes = 0;
   }
   void* p = nullptr;
   cudaError_t err = cudaMalloc(&p, bytes);
@@ -353,8 +401,8 @@ int ensure_ws(b200sr_engine* e, size_t bytes, cudaStream_t st) {
     cudaGetLastError();
     return fail(e, B200SR_ERR_OOM, std::string("out of memory allocating ") + std::to_string(bytes >> 20) + " MiB workspace");
   }
-  e->ws = static_cast<uint8_t*>(p);
-  e->ws_bytes = bytes;
+  lane->ws = static_cast<uint8_t*>(p);
+  lane->ws_bytes = bytes;
   return B200SR_OK;
 }
 
@@ -413,24 +461,28 @@ void build_rdb_items(int N, int H, int W, std::vector<RdbItem>& items, int* nfla
       }
 }
 
-int ensure_rdb_table(b200sr_engine* e, int N, int H, int W, cudaStream_t st) {
-  if (e->d_rdb_items && e->rdb_n == N && e->rdb_h == H && e->rdb_w == W) return B200SR_OK;
+int ensure_rdb_table(b200sr_engine* e, Lane* lane, int N, int H, int W, cudaStream_t st) {
+  if (lane->d_rdb_items && lane->rdb_n == N && lane->rdb_h == H && lane->rdb_w == W && lane->rdb_gen == e->rdb_gen)
+    return B200SR_OK;
   CUDA_TRY(e, cudaStreamSynchronize(st));
-  if (e->d_rdb_items) cudaFree(e->d_rdb_items);
-  if (e->d_rdb_flags) cudaFree(e->d_rdb_flags);
-  e->d_rdb_items = nullptr;
-  e->d_rdb_flags = nullptr;
+  if (lane->d_rdb_items) cudaFree(lane->d_rdb_items);
+  if (lane->d_rdb_flags) cudaFree(lane->d_rdb_flags);
+  lane->d_rdb_items = nullptr;
+  lane->d_rdb_flags = nullptr;
   std::vector<RdbItem> items;
   int nflags = 0;
   build_rdb_items(N, H, W, items, &nflags);
-  CUDA_TRY(e, cudaMalloc(&e->d_rdb_items, items.size() * sizeof(RdbItem)));
-  CUDA_TRY(e, cudaMalloc(&e->d_rdb_flags, static_cast<size_t>(nflags + 1) * sizeof(int)));   // + item counter
-  CUDA_TRY(e, cudaMemcpy(e->d_rdb_items, items.data(), items.size() * sizeof(RdbItem), cudaMemcpyHostToDevice));
-  e->rdb_n = N;
-  e->rdb_h = H;
-  e->rdb_w = W;
-  e->rdb_nitems = static_cast<int>(items.size());
-  e->rdb_nflags = nflags;
+  CUDA_TRY(e, cudaMalloc(&lane->d_rdb_items, items.size() * sizeof(RdbItem)));
+  CUDA_TRY(e, cudaMalloc(&lane->d_rdb_flags, static_cast<size_t>(nflags + 1) * sizeof(int)));   // + item counter
+  // pageable source: the copy is staged before the call returns, so `items` may go out of scope
+  CUDA_TRY(e, cudaMemcpyAsync(lane->d_rdb_items, items.data(), items.size() * sizeof(RdbItem), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(e, cudaStreamSynchronize(st));
+  lane->rdb_n = N;
+  lane->rdb_h = H;
+  lane->rdb_w = W;
+  lane->rdb_gen = e->rdb_gen;
+  lane->rdb_nitems = static_cast<int>(items.size());
+  lane->rdb_nflags = nflags;
   return B200SR_OK;
 }
 
@@ -442,9 +494,9 @@ struct TrunkIO {   // residual-stream operands of one RDB's conv5 (TrunkLo, conv
   const uint8_t* xb_lo;
 };
 
-int launch_rdb_fused(b200sr_engine* e, int li, bool rrdb_end, __nv_bfloat16* Dcur, __nv_bfloat16* Dnext,
+int launch_rdb_fused(b200sr_engine* e, Lane* lane, int li, bool rrdb_end, __nv_bfloat16* Dcur, __nv_bfloat16* Dnext,
                      const TrunkIO& tio, int N, int H, int W, cudaStream_t st) {
-  int rc = ensure_rdb_table(e, N, H, W, st);
+  int rc = ensure_rdb_table(e, lane, N, H, W, st);
   if (rc) return rc;
   CUtensorMap amap;
   if (!tmap_encode_act(&amap, Dcur, 3 * N, H, W, 64, 64, 130, 128)) return fail(e, B200SR_ERR_CUDA, "cuTensorMapEncodeTiled failed");
@@ -479,25 +531,31 @@ int launch_rdb_fused(b200sr_engine* e, int li, bool rrdb_end, __nv_bfloat16* Dcu
     }
     flops += 2.0 * 9.0 * l.cin * l.cout * static_cast<double>(N) * H * W;
   }
-  a.items = e->d_rdb_items;
-  a.nitems = e->rdb_nitems;
-  a.flags = e->d_rdb_flags;
-  a.counter = e->d_rdb_flags + e->rdb_nflags;
+  a.items = lane->d_rdb_items;
+  a.nitems = lane->rdb_nitems;
+  a.flags = lane->d_rdb_flags;
+  a.counter = lane->d_rdb_flags + lane->rdb_nflags;
   a.flag_target = ((W + 127) / 128) * RDB_NEPI_WARPS;
   a.rrdb_end = rrdb_end ? 1 : 0;
-  ++e->rdb_launch_idx;
-  if (e->rdb_launch_idx == -e->opt_rdb_stats) {   // negative: cycle counters only (no per-item / per-row stamps)
+  ++lane->rdb_launch_idx;
+  if (lane->rdb_launch_idx == -e->opt_rdb_stats) {   // negative: cycle counters only (no per-item / per-row stamps)
     if (!e->d_rdb_stats) CUDA_TRY(e, cudaMalloc(&e->d_rdb_stats, 148 * 16 * sizeof(long long)));
     a.stats = e->d_rdb_stats;
   }
-  if (e->rdb_launch_idx == e->opt_rdb_stats) {
+  if (e->opt_rdb_stats > 0 && lane->rdb_launch_idx == e->opt_rdb_stats) {   // dev tool, single-threaded use only
     if (!e->d_rdb_stats) CUDA_TRY(e, cudaMalloc(&e->d_rdb_stats, 148 * 16 * sizeof(long long)));
     a.stats = e->d_rdb_stats;
-    if (!e->d_rdb_trace) CUDA_TRY(e, cudaMalloc(&e->d_rdb_trace, static_cast<size_t>(e->rdb_nitems) * 10 * sizeof(long long)));
-    CUDA_TRY(e, cudaMemsetAsync(e->d_rdb_trace, 0, static_cast<size_t>(e->rdb_nitems) * 10 * sizeof(long long), st));
+    if (e->stats_nitems != lane->rdb_nitems) {
+      if (e->d_rdb_trace) cudaFree(e->d_rdb_trace);
+      if (e->d_rdb_trace2) cudaFree(e->d_rdb_trace2);
+      e->d_rdb_trace = e->d_rdb_trace2 = nullptr;
+      e->stats_nitems = lane->rdb_nitems;
+    }
+    if (!e->d_rdb_trace) CUDA_TRY(e, cudaMalloc(&e->d_rdb_trace, static_cast<size_t>(lane->rdb_nitems) * 10 * sizeof(long long)));
+    CUDA_TRY(e, cudaMemsetAsync(e->d_rdb_trace, 0, static_cast<size_t>(lane->rdb_nitems) * 10 * sizeof(long long), st));
     a.trace = e->d_rdb_trace;
-    if (!e->d_rdb_trace2) CUDA_TRY(e, cudaMalloc(&e->d_rdb_trace2, static_cast<size_t>(e->rdb_nitems) * 48 * sizeof(long long)));
-    CUDA_TRY(e, cudaMemsetAsync(e->d_rdb_trace2, 0, static_cast<size_t>(e->rdb_nitems) * 48 * sizeof(long long), st));
+    if (!e->d_rdb_trace2) CUDA_TRY(e, cudaMalloc(&e->d_rdb_trace2, static_cast<size_t>(lane->rdb_nitems) * 48 * sizeof(long long)));
+    CUDA_TRY(e, cudaMemsetAsync(e->d_rdb_trace2, 0, static_cast<size_t>(lane->rdb_nitems) * 48 * sizeof(long long), st));
     a.trace2 = e->d_rdb_trace2;
   }
   static bool attr_done[16] = {};
@@ -506,15 +564,15 @@ int launch_rdb_fused(b200sr_engine* e, int li, bool rrdb_end, __nv_bfloat16* Dcu
     attr_done[e->device & 15] = true;
   }
   ProfScope prof_scope(e, PC_RDB_FUSED, flops, st);
-  CUDA_TRY(e, cudaMemsetAsync(e->d_rdb_flags, 0, static_cast<size_t>(e->rdb_nflags + 1) * sizeof(int), st));
+  CUDA_TRY(e, cudaMemsetAsync(lane->d_rdb_flags, 0, static_cast<size_t>(lane->rdb_nflags + 1) * sizeof(int), st));
   const int grid = std::min(a.nitems, e->opt_max_ctas > 0 ? e->opt_max_ctas : e->num_sms);
   rdb_fused_kernel<<<grid, RDB_NTHREADS, RDB_SMEM_BYTES, st>>>(amap, a);
   CUDA_TRY(e, cudaGetLastError());
-  e->launches++;
+  lane->launches++;
   return B200SR_OK;
 }
 
-int run_first(b200sr_engine* e, const Region& R, int s, int H, int W, __nv_bfloat16* out, int out_pitch, int out_fp16,
+int run_first(b200sr_engine* e, Lane* lane, const Region& R, int s, int H, int W, __nv_bfloat16* out, int out_pitch, int out_fp16,
               uint8_t* lo, float* f0, float* inrgb, const float* prelu, cudaStream_t st) {
   const Layer& l = e->layers[0];
   FirstArgs a{};
@@ -550,17 +608,17 @@ int run_first(b200sr_engine* e, const Region& R, int s, int H, int W, __nv_bfloa
     first_conv_kernel<12><<<grid, 128, sm, st>>>(a);
   }
   CUDA_TRY(e, cudaGetLastError());
-  e->launches++;
+  lane->launches++;
   return B200SR_OK;
 }
 
-int run_upsample(b200sr_engine* e, const void* in, void* out, int N, int H, int W, cudaStream_t st) {
+int run_upsample(b200sr_engine* e, Lane* lane, const void* in, void* out, int N, int H, int W, cudaStream_t st) {
   const size_t total = static_cast<size_t>(N) * 2 * H * 2 * W * 8;
   const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(e->num_sms) * 16));
   ProfScope prof_scope(e, PC_UPSAMPLE, 0.0, st);
   upsample2x_kernel<<<grid, 256, 0, st>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), N, H, W);
   CUDA_TRY(e, cudaGetLastError());
-  e->launches++;
+  lane->launches++;
   return B200SR_OK;
 }
 
@@ -617,15 +675,15 @@ std::vector<Region> plan_regions(int arch, int scale, int h, int w, int tile, in
 }
 
 // One forward pass over one region (whole padded frame, or one padded tile).
-int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
+int run_region(b200sr_engine* e, Lane* lane, const Region& R, cudaStream_t st) {
   const auto& d = e->desc;
   const int s = (d.arch == B200SR_ARCH_RRDB && d.scale == 2) ? 2 : 1;
   if (R.rh % s || R.rw % s) return fail(e, B200SR_ERR_INVALID, "region size not divisible by the unshuffle factor");
   const int N = R.n, H = R.rh / s, W = R.rw / s;
   const size_t px = static_cast<size_t>(N) * H * W;
-  int rc = ensure_ws(e, region_ws_bytes(e, N, H, W), st);
+  int rc = ensure_ws(e, lane, region_ws_bytes(e, N, H, W), st);
   if (rc) return rc;
-  uint8_t* cur = e->ws;
+  uint8_t* cur = lane->ws;
   auto take = [&](size_t b) {
     uint8_t* p = cur;
     cur += align_up(b, 1024);
@@ -651,6 +709,9 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
     // 128 B access).  RDB r of every RRDB reads D[r] and writes the next x.hi into plane 0 of D[(r + 1) % 3]; D[0]
     // therefore still holds the RRDB input x0.hi when the third RDB needs it, and is overwritten pixel by pixel
     // by the thread that has just read it.
+    const int TG = tail_group(N, H, W);
+    const size_t fpx = static_cast<size_t>(H) * W;          // pixels per frame
+    const size_t tpx = static_cast<size_t>(TG) * fpx;
     __nv_bfloat16* D[3];
     for (int i = 0; i < 3; ++i) D[i] = reinterpret_cast<__nv_bfloat16*>(take(px * 192 * 2));
     const size_t pxt = static_cast<size_t>(N) * H * ((W + 127) / 128) * 128;
@@ -658,13 +719,13 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
     uint8_t* loB = take(pxt * 64);   // x0.lo (RRDB input), rewritten in place at the RRDB end
     float* f0 = reinterpret_cast<float*>(take(pxt * 64 * 4));
     __nv_bfloat16* U0 = reinterpret_cast<__nv_bfloat16*>(take(px * 64 * 2));
-    __nv_bfloat16* U1 = reinterpret_cast<__nv_bfloat16*>(take(px * 4 * 64 * 2));
-    __nv_bfloat16* U2 = reinterpret_cast<__nv_bfloat16*>(take(px * 4 * 64 * 2));
-    __nv_bfloat16* U3 = reinterpret_cast<__nv_bfloat16*>(take(px * 16 * 64 * 2));
-    __nv_bfloat16* U4 = reinterpret_cast<__nv_bfloat16*>(take(px * 16 * 64 * 2));
+    __nv_bfloat16* U1 = reinterpret_cast<__nv_bfloat16*>(take(tpx * 4 * 64 * 2));
+    __nv_bfloat16* U2 = reinterpret_cast<__nv_bfloat16*>(take(tpx * 4 * 64 * 2));
+    __nv_bfloat16* U3 = reinterpret_cast<__nv_bfloat16*>(take(tpx * 16 * 64 * 2));
+    __nv_bfloat16* U4 = reinterpret_cast<__nv_bfloat16*>(take(tpx * 16 * 64 * 2));
 
     const size_t plane = px * 64;
-    rc = run_first(e, R, s, H, W, D[0], 64, 0, loB, f0, nullptr, nullptr, st);
+    rc = run_first(e, lane, R, s, H, W, D[0], 64, 0, loB, f0, nullptr, nullptr, st);
     if (rc) return rc;
     int li = 1;
     const int cur_d = 0;   // the trunk ends where it started
@@ -678,7 +739,7 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
         tio.xb_hi = D[0];
         tio.xb_lo = loB;
         if (e->opt_fused_rdb) {
-          rc = launch_rdb_fused(e, li, r == 2, Din, Dout, tio, N, H, W, st);
+          rc = launch_rdb_fused(e, lane, li, r == 2, Din, Dout, tio, N, H, W, st);
           if (rc) return rc;
           li += 5;
         } else {
@@ -689,7 +750,7 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
             a.out = Din + (1 + k / 2) * plane;
             a.out_pitch = 64;
             a.out_choff = 32 * (k & 1);
-            rc = launch_conv(e, e->layers[li++], EPI_ACT_BF16, io, a, st);
+            rc = launch_conv(e, lane, e->layers[li++], EPI_ACT_BF16, io, a, st);
             if (rc) return rc;
           }
           ConvArgs a = base;
@@ -701,7 +762,7 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
           a.lo_out = tio.lo_out;
           a.xb_hi = tio.xb_hi;
           a.xb_lo = tio.xb_lo;
-          rc = launch_conv(e, e->layers[li++], r == 2 ? EPI_RDB5_RRDB : EPI_RDB5, io, a, st);
+          rc = launch_conv(e, lane, e->layers[li++], r == 2 ? EPI_RDB5_RRDB : EPI_RDB5, io, a, st);
           if (rc) return rc;
         }
       }
@@ -712,60 +773,72 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
       a.out_pitch = 64;
       a.out_fp16 = 1;
       a.fadd = f0;
-      rc = launch_conv(e, e->layers[li++], EPI_ADD_F32, io, a, st);
+      rc = launch_conv(e, lane, e->layers[li++], EPI_ADD_F32, io, a, st);
       if (rc) return rc;
     }
-    // conv_up1/conv_up2 read F.interpolate(x, 2, 'nearest') of their input straight from the low-resolution
-    // tensor through the duplicated-pixel TMA view (option fold_up = 0: materialise it with upsample2x_kernel)
-    if (!e->opt_fold_up) {
-      rc = run_upsample(e, U0, U1, N, H, W, st);
-      if (rc) return rc;
-    }
-    {  // conv_up1 + lrelu
-      ConvIO io{e->opt_fold_up ? U0 : U1, 64, N, 2 * H, 2 * W, 0, e->opt_fold_up};
-      ConvArgs a = base;
-      a.slope = 0.2f;
-      a.out = U2;
-      a.out_pitch = 64;
-      a.out_fp16 = 1;
-      rc = launch_conv(e, e->layers[li++], EPI_ACT_BF16, io, a, st);
-      if (rc) return rc;
-    }
-    if (!e->opt_fold_up) {
-      rc = run_upsample(e, U2, U3, N, 2 * H, 2 * W, st);
-      if (rc) return rc;
-    }
-    {  // conv_up2 + lrelu
-      ConvIO io{e->opt_fold_up ? U2 : U3, 64, N, 4 * H, 4 * W, 0, e->opt_fold_up};
-      ConvArgs a = base;
-      a.slope = 0.2f;
-      a.out = U4;
-      a.out_pitch = 64;
-      a.out_fp16 = 1;
-      rc = launch_conv(e, e->layers[li++], EPI_ACT_BF16, io, a, st);
-      if (rc) return rc;
-    }
-    {  // conv_hr + lrelu
-      ConvIO io{U4, 64, N, 4 * H, 4 * W};
-      ConvArgs a = base;
-      a.slope = 0.2f;
-      a.out = U3;
-      a.out_pitch = 64;
-      a.out_fp16 = 1;
-      rc = launch_conv(e, e->layers[li++], EPI_ACT_BF16, io, a, st);
-      if (rc) return rc;
-    }
-    {  // conv_last + clamp/round/quantise + crop
-      ConvIO io{U3, 64, N, 4 * H, 4 * W};
-      rc = launch_conv(e, e->layers[li++], EPI_LAST_U8, io, base, st);
-      if (rc) return rc;
+    // HR tail, TG frames at a time.  conv_up1/conv_up2 read F.interpolate(x, 2, 'nearest') of their input straight
+    // from the low-resolution tensor through the duplicated-pixel TMA view (option fold_up = 0: materialise it
+    // with upsample2x_kernel).
+    const Layer& l_up1 = e->layers[li];
+    const Layer& l_up2 = e->layers[li + 1];
+    const Layer& l_hr = e->layers[li + 2];
+    const Layer& l_last = e->layers[li + 3];
+    const size_t dst_frame = static_cast<size_t>(R.dst_h) * R.dst_w * 3 * (R.sample16 ? 2 : 1);
+    for (int f0i = 0; f0i < N; f0i += TG) {
+      const int n = std::min(TG, N - f0i);
+      const __nv_bfloat16* U0f = U0 + static_cast<size_t>(f0i) * fpx * 64;
+      ConvArgs tb = base;
+      tb.dst = R.dst + static_cast<size_t>(f0i) * dst_frame;
+      if (!e->opt_fold_up) {
+        rc = run_upsample(e, lane, U0f, U1, n, H, W, st);
+        if (rc) return rc;
+      }
+      {  // conv_up1 + lrelu
+        ConvIO io{e->opt_fold_up ? static_cast<const void*>(U0f) : U1, 64, n, 2 * H, 2 * W, 0, e->opt_fold_up};
+        ConvArgs a = tb;
+        a.slope = 0.2f;
+        a.out = U2;
+        a.out_pitch = 64;
+        a.out_fp16 = 1;
+        rc = launch_conv(e, lane, l_up1, EPI_ACT_BF16, io, a, st);
+        if (rc) return rc;
+      }
+      if (!e->opt_fold_up) {
+        rc = run_upsample(e, lane, U2, U3, n, 2 * H, 2 * W, st);
+        if (rc) return rc;
+      }
+      {  // conv_up2 + lrelu
+        ConvIO io{e->opt_fold_up ? U2 : U3, 64, n, 4 * H, 4 * W, 0, e->opt_fold_up};
+        ConvArgs a = tb;
+        a.slope = 0.2f;
+        a.out = U4;
+        a.out_pitch = 64;
+        a.out_fp16 = 1;
+        rc = launch_conv(e, lane, l_up2, EPI_ACT_BF16, io, a, st);
+        if (rc) return rc;
+      }
+      {  // conv_hr + lrelu
+        ConvIO io{U4, 64, n, 4 * H, 4 * W};
+        ConvArgs a = tb;
+        a.slope = 0.2f;
+        a.out = U3;
+        a.out_pitch = 64;
+        a.out_fp16 = 1;
+        rc = launch_conv(e, lane, l_hr, EPI_ACT_BF16, io, a, st);
+        if (rc) return rc;
+      }
+      {  // conv_last + clamp/round/quantise + crop
+        ConvIO io{U3, 64, n, 4 * H, 4 * W};
+        rc = launch_conv(e, lane, l_last, EPI_LAST_U8, io, tb, st);
+        if (rc) return rc;
+      }
     }
   } else {
     __nv_bfloat16* S[2];
     S[0] = reinterpret_cast<__nv_bfloat16*>(take(px * 64 * 2));
     S[1] = reinterpret_cast<__nv_bfloat16*>(take(px * 64 * 2));
     float* inrgb = reinterpret_cast<float*>(take(px * 4 * 4));
-    rc = run_first(e, R, 1, H, W, S[0], 64, 1, nullptr, nullptr, inrgb, e->prelu_dev[0], st);
+    rc = run_first(e, lane, R, 1, H, W, S[0], 64, 1, nullptr, nullptr, inrgb, e->prelu_dev[0], st);
     if (rc) return rc;
     int cur_s = 0;
     for (int i = 0; i < d.num_block; ++i) {
@@ -775,14 +848,14 @@ int run_region(b200sr_engine* e, const Region& R, cudaStream_t st) {
       a.out_pitch = 64;
       a.out_fp16 = 1;
       a.prelu = e->prelu_dev[i + 1];
-      rc = launch_conv(e, e->layers[1 + i], EPI_PRELU_BF16, io, a, st);
+      rc = launch_conv(e, lane, e->layers[1 + i], EPI_PRELU_BF16, io, a, st);
       if (rc) return rc;
       cur_s ^= 1;
     }
     ConvIO io{S[cur_s], 64, N, H, W};
     ConvArgs a = base;
     a.fadd = inrgb;
-    rc = launch_conv(e, e->layers[1 + d.num_block], EPI_SRVGG_LAST, io, a, st);
+    rc = launch_conv(e, lane, e->layers[1 + d.num_block], EPI_SRVGG_LAST, io, a, st);
     if (rc) return rc;
   }
   return B200SR_OK;
@@ -795,7 +868,16 @@ extern "C" {
 
 const char* b200sr_version(void) { return "b200sr 0.1 (sm_100a, tcgen05/TMEM/TMA)"; }
 
-const char* b200sr_last_error(const b200sr_engine* e) { return e ? e->err.c_str() : "null engine"; }
+// Message of the last failed call made by THIS thread (engines are shared between threads); falls back to the
+// engine's most recent message.
+const char* b200sr_last_error(const b200sr_engine* e) {
+  if (!e) return "null engine";
+  if (tls_err.empty()) {
+    std::lock_guard<std::mutex> g(const_cast<b200sr_engine*>(e)->mu);
+    tls_err = e->err;
+  }
+  return tls_err.c_str();
+}
 
 int b200sr_create(const b200sr_model_desc* desc, int device, b200sr_engine** out) {
   if (!desc || !out) return B200SR_ERR_INVALID;
@@ -829,6 +911,18 @@ int b200sr_create(const b200sr_model_desc* desc, int device, b200sr_engine** out
   return B200SR_OK;
 }
 
+static void free_lane(Lane* l) {
+  if (l->ws) cudaFree(l->ws);
+  if (l->d_rdb_items) cudaFree(l->d_rdb_items);
+  if (l->d_rdb_flags) cudaFree(l->d_rdb_flags);
+  if (l->dev_in) cudaFree(l->dev_in);
+  if (l->dev_out) cudaFree(l->dev_out);
+  if (l->pin_in) cudaFreeHost(l->pin_in);
+  if (l->pin_out) cudaFreeHost(l->pin_out);
+  if (l->stream) cudaStreamDestroy(l->stream);
+  *l = Lane{};
+}
+
 void b200sr_destroy(b200sr_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
@@ -840,15 +934,11 @@ void b200sr_destroy(b200sr_engine* e) {
   }
   for (auto* p : e->prelu_dev)
     if (p) cudaFree(p);
-  if (e->ws) cudaFree(e->ws);
-  if (e->d_rdb_items) cudaFree(e->d_rdb_items);
-  if (e->d_rdb_flags) cudaFree(e->d_rdb_flags);
+  free_lane(&e->dev_lane);
+  for (auto& l : e->lanes) free_lane(l.get());
   if (e->d_rdb_stats) cudaFree(e->d_rdb_stats);
   if (e->d_rdb_trace) cudaFree(e->d_rdb_trace);
   if (e->d_rdb_trace2) cudaFree(e->d_rdb_trace2);
-  if (e->stage_in) cudaFree(e->stage_in);
-  if (e->stage_out) cudaFree(e->stage_out);
-  if (e->own_stream) cudaStreamDestroy(e->own_stream);
   for (auto& r : e->prof) {
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
@@ -944,8 +1034,8 @@ int b200sr_workspace_bytes(b200sr_engine* e, int n, int h, int w, int tile, int 
   return B200SR_OK;
 }
 
-static int enqueue_impl(b200sr_engine* e, const void* src_dev_v, void* dst_dev_v, int n, int h, int w, int tile,
-                        int tile_pad, int pre_pad, void* cuda_stream, int sample16) {
+static int enqueue_impl(b200sr_engine* e, Lane* lane, const void* src_dev_v, void* dst_dev_v, int n, int h, int w,
+                        int tile, int tile_pad, int pre_pad, void* cuda_stream, int sample16) {
   const uint8_t* src_dev = static_cast<const uint8_t*>(src_dev_v);
   uint8_t* dst_dev = static_cast<uint8_t*>(dst_dev_v);
   if (!e) return B200SR_ERR_INVALID;
@@ -955,8 +1045,8 @@ static int enqueue_impl(b200sr_engine* e, const void* src_dev_v, void* dst_dev_v
   if (pre_pad >= h || pre_pad >= w) return fail(e, B200SR_ERR_INVALID, "pre_pad must be smaller than the frame (reflect padding)");
   CUDA_TRY(e, cudaSetDevice(e->device));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  e->launches = 0;
-  e->rdb_launch_idx = 0;
+  lane->launches = 0;
+  lane->rdb_launch_idx = 0;
   const int scale = e->desc.scale;
   int Hp, Wp;
   padded_dims(e, h, w, pre_pad, &Hp, &Wp);
@@ -968,49 +1058,169 @@ static int enqueue_impl(b200sr_engine* e, const void* src_dev_v, void* dst_dev_v
     R.dst = dst_dev;
     R.sample16 = sample16;
     R.n = n;
-    int rc = run_region(e, R, st);
+    int rc = run_region(e, lane, R, st);
     if (rc) return rc;
   }
+  e->last_launches.store(lane->launches);
   return B200SR_OK;
 }
 
+// Device-pointer entry points: asynchronous on the caller's stream, on the engine's device lane.  Calls on one
+// engine must be ordered with each other by the caller (same stream, or events), as with any stream-ordered API.
 int b200sr_enqueue_u8(b200sr_engine* e, const uint8_t* src_dev, uint8_t* dst_dev, int n, int h, int w, int tile,
                       int tile_pad, int pre_pad, void* cuda_stream) {
-  return enqueue_impl(e, src_dev, dst_dev, n, h, w, tile, tile_pad, pre_pad, cuda_stream, 0);
+  if (!e) return B200SR_ERR_INVALID;
+  return enqueue_impl(e, &e->dev_lane, src_dev, dst_dev, n, h, w, tile, tile_pad, pre_pad, cuda_stream, 0);
 }
 
 int b200sr_enqueue_u16(b200sr_engine* e, const uint16_t* src_dev, uint16_t* dst_dev, int n, int h, int w, int tile,
                        int tile_pad, int pre_pad, void* cuda_stream) {
-  return enqueue_impl(e, src_dev, dst_dev, n, h, w, tile, tile_pad, pre_pad, cuda_stream, 1);
+  if (!e) return B200SR_ERR_INVALID;
+  return enqueue_impl(e, &e->dev_lane, src_dev, dst_dev, n, h, w, tile, tile_pad, pre_pad, cuda_stream, 1);
 }
 
+// ---- host-buffer entry point: pipelined over the engine's lanes ---------------------------------------------------
+namespace {
+
+bool host_ptr_is_pinned(const void* p) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+Lane* acquire_lane(b200sr_engine* e, bool block) {
+  std::unique_lock<std::mutex> lk(e->mu);
+  while (static_cast<int>(e->lanes.size()) < std::max(1, e->opt_lanes)) {
+    e->lanes.emplace_back(new Lane());
+    e->lanes.back()->id = static_cast<int>(e->lanes.size());
+  }
+  while (true) {
+    for (auto& l : e->lanes)
+      if (!l->busy) {
+        l->busy = true;
+        return l.get();
+      }
+    if (!block) return nullptr;
+    e->cv.wait(lk);
+  }
+}
+
+void release_lane(b200sr_engine* e, Lane* l) {
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    l->busy = false;
+  }
+  e->cv.notify_one();
+}
+
+int grow_dev(b200sr_engine* e, uint8_t** p, size_t* have, size_t need) {
+  if (need <= *have) return B200SR_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *have = 0;
+  CUDA_TRY(e, cudaMalloc(p, need));
+  *have = need;
+  return B200SR_OK;
+}
+
+int grow_pinned(b200sr_engine* e, uint8_t** p, size_t* have, size_t need) {
+  if (need <= *have) return B200SR_OK;
+  if (*p) cudaFreeHost(*p);
+  *p = nullptr;
+  *have = 0;
+  CUDA_TRY(e, cudaHostAlloc(p, need, cudaHostAllocPortable));
+  *have = need;
+  return B200SR_OK;
+}
+
+struct HostJob {
+  Lane* lane;
+  int f0, cnt;
+};
+
+}  // namespace
+
+// n frames from host memory to host memory.  The frames are cut into jobs of `chunk` frames; every job takes a free
+// lane and queues H2D copy -> forward pass -> D2H copy on that lane's stream, so job k+1's upload and job k-1's
+// download overlap job k's kernels (two lanes = double buffering), and so do the jobs of concurrent callers.
+// Pinned (cudaHostAlloc / cudaHostRegister) buffers are copied directly; pageable ones are staged through the
+// lane's pinned buffers.  Deadlock-free: a caller blocks for a lane only while it holds none.
 static int upscale_host_impl(b200sr_engine* e, const void* src_host, void* dst_host, int n, int h, int w, int tile,
                              int tile_pad, int pre_pad, int sample16) {
   if (!e || !src_host || !dst_host || n <= 0 || h <= 0 || w <= 0) return B200SR_ERR_INVALID;
+  if (!e->finalized) return fail(e, B200SR_ERR_STATE, "weights not finalised");
   CUDA_TRY(e, cudaSetDevice(e->device));
-  if (!e->own_stream) CUDA_TRY(e, cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
-  const size_t in_bytes = static_cast<size_t>(n) * h * w * 3 * (sample16 ? 2 : 1);
-  const size_t out_bytes = in_bytes * e->desc.scale * e->desc.scale;
-  if (in_bytes > e->stage_in_bytes) {
-    if (e->stage_in) cudaFree(e->stage_in);
-    e->stage_in = nullptr;
-    e->stage_in_bytes = 0;
-    CUDA_TRY(e, cudaMalloc(&e->stage_in, in_bytes));
-    e->stage_in_bytes = in_bytes;
+  const size_t in_frame = static_cast<size_t>(h) * w * 3 * (sample16 ? 2 : 1);
+  const size_t out_frame = in_frame * e->desc.scale * e->desc.scale;
+  const bool src_pinned = host_ptr_is_pinned(src_host), dst_pinned = host_ptr_is_pinned(dst_host);
+  // frames per job: ~two 720p frames of pixels keeps the persistent kernels' launch tails short relative to the
+  // job while two lanes in flight hide them (measured flat from there up)
+  int chunk = e->opt_host_chunk;
+  if (chunk <= 0) chunk = static_cast<int>(std::max<long>(1, (2L * 1280 * 720) / (static_cast<long>(h) * w)));
+  chunk = std::min(chunk, n);
+  const uint8_t* src = static_cast<const uint8_t*>(src_host);
+  uint8_t* dst = static_cast<uint8_t*>(dst_host);
+  std::deque<HostJob> inflight;
+  int status = B200SR_OK;
+  int launches = 0;
+
+  auto retire = [&](const HostJob& j, bool copy_out) {
+    cudaError_t err = cudaStreamSynchronize(j.lane->stream);
+    if (err != cudaSuccess && status == B200SR_OK)
+      status = fail(e, err == cudaErrorMemoryAllocation ? B200SR_ERR_OOM : B200SR_ERR_CUDA,
+                    std::string("cudaStreamSynchronize: ") + cudaGetErrorString(err));
+    if (copy_out && status == B200SR_OK && !dst_pinned)
+      memcpy(dst + static_cast<size_t>(j.f0) * out_frame, j.lane->pin_out, static_cast<size_t>(j.cnt) * out_frame);
+    launches += j.lane->launches;
+    release_lane(e, j.lane);
+  };
+  auto submit = [&](Lane* L, int f0, int cnt) -> int {
+    if (!L->stream) CUDA_TRY(e, cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
+    const size_t ib = static_cast<size_t>(cnt) * in_frame, ob = static_cast<size_t>(cnt) * out_frame;
+    int rc = grow_dev(e, &L->dev_in, &L->dev_in_bytes, ib);
+    if (!rc) rc = grow_dev(e, &L->dev_out, &L->dev_out_bytes, ob);
+    if (!rc && !src_pinned) rc = grow_pinned(e, &L->pin_in, &L->pin_in_bytes, ib);
+    if (!rc && !dst_pinned) rc = grow_pinned(e, &L->pin_out, &L->pin_out_bytes, ob);
+    if (rc) return rc;
+    const uint8_t* sp = src + static_cast<size_t>(f0) * in_frame;
+    if (!src_pinned) {
+      memcpy(L->pin_in, sp, ib);
+      sp = L->pin_in;
+    }
+    CUDA_TRY(e, cudaMemcpyAsync(L->dev_in, sp, ib, cudaMemcpyHostToDevice, L->stream));
+    rc = enqueue_impl(e, L, L->dev_in, L->dev_out, cnt, h, w, tile, tile_pad, pre_pad, L->stream, sample16);
+    if (rc) return rc;
+    uint8_t* dp = dst_pinned ? dst + static_cast<size_t>(f0) * out_frame : L->pin_out;
+    CUDA_TRY(e, cudaMemcpyAsync(dp, L->dev_out, ob, cudaMemcpyDeviceToHost, L->stream));
+    return B200SR_OK;
+  };
+
+  for (int f0 = 0; f0 < n && status == B200SR_OK; f0 += chunk) {
+    const int cnt = std::min(chunk, n - f0);
+    Lane* L = inflight.empty() ? acquire_lane(e, true) : acquire_lane(e, false);
+    while (!L) {   // every lane is busy and this call holds some: finish our oldest job first
+      retire(inflight.front(), true);
+      inflight.pop_front();
+      L = inflight.empty() ? acquire_lane(e, true) : acquire_lane(e, false);
+    }
+    const int rc = submit(L, f0, cnt);
+    if (rc) {
+      status = rc;
+      cudaStreamSynchronize(L->stream);
+      release_lane(e, L);
+      break;
+    }
+    inflight.push_back(HostJob{L, f0, cnt});
   }
-  if (out_bytes > e->stage_out_bytes) {
-    if (e->stage_out) cudaFree(e->stage_out);
-    e->stage_out = nullptr;
-    e->stage_out_bytes = 0;
-    CUDA_TRY(e, cudaMalloc(&e->stage_out, out_bytes));
-    e->stage_out_bytes = out_bytes;
+  while (!inflight.empty()) {
+    retire(inflight.front(), true);
+    inflight.pop_front();
   }
-  CUDA_TRY(e, cudaMemcpyAsync(e->stage_in, src_host, in_bytes, cudaMemcpyHostToDevice, e->own_stream));
-  int rc = enqueue_impl(e, e->stage_in, e->stage_out, n, h, w, tile, tile_pad, pre_pad, e->own_stream, sample16);
-  if (rc) return rc;
-  CUDA_TRY(e, cudaMemcpyAsync(dst_host, e->stage_out, out_bytes, cudaMemcpyDeviceToHost, e->own_stream));
-  CUDA_TRY(e, cudaStreamSynchronize(e->own_stream));
-  return B200SR_OK;
+  if (status == B200SR_OK) e->last_launches.store(launches);
+  return status;
 }
 
 int b200sr_upscale_host_u8(b200sr_engine* e, const uint8_t* src_host, uint8_t* dst_host, int n, int h, int w, int tile,
@@ -1023,7 +1233,37 @@ int b200sr_upscale_host_u16(b200sr_engine* e, const uint16_t* src_host, uint16_t
   return upscale_host_impl(e, src_host, dst_host, n, h, w, tile, tile_pad, pre_pad, 1);
 }
 
-int b200sr_last_launch_count(const b200sr_engine* e) { return e ? e->launches : 0; }
+// Pinned host memory for callers that want zero-copy staging (the Python layer allocates `enhance`'s result arrays
+// here, and the multi-GPU scheduler registers its shared-memory frame rings).
+void* b200sr_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void b200sr_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+int b200sr_host_register(void* p, size_t bytes) {
+  if (!p || bytes == 0) return B200SR_ERR_INVALID;
+  if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return B200SR_ERR_CUDA;
+  }
+  return B200SR_OK;
+}
+int b200sr_host_unregister(void* p) {
+  if (!p) return B200SR_ERR_INVALID;
+  if (cudaHostUnregister(p) != cudaSuccess) {
+    cudaGetLastError();
+    return B200SR_ERR_CUDA;
+  }
+  return B200SR_OK;
+}
+
+int b200sr_last_launch_count(const b200sr_engine* e) { return e ? e->last_launches.load() : 0; }
 
 int b200sr_set_option(b200sr_engine* e, const char* key, int value) {
   if (!e || !key) return B200SR_ERR_INVALID;
@@ -1040,12 +1280,12 @@ int b200sr_set_option(b200sr_engine* e, const char* key, int value) {
     RDB_STEP_OFF[2] = (value / 100) % 100;
     RDB_STEP_OFF[3] = (value / 10000) % 100;
     RDB_STEP_OFF[4] = (value / 1000000) % 100;
-    e->rdb_n = 0;   // rebuild the work list
+    e->rdb_gen++;   // lanes rebuild their work lists
     return B200SR_OK;
   }
   if (!strcmp(key, "rdb_interleave")) {
     RDB_INTERLEAVE = value;
-    e->rdb_n = -1;   // rebuild the work list
+    e->rdb_gen++;
     return B200SR_OK;
   }
   if (!strcmp(key, "rdb_order")) {   // five decimal digits, e.g. 32104
@@ -1054,7 +1294,7 @@ int b200sr_set_option(b200sr_engine* e, const char* key, int value) {
       RDB_ORDER[i] = v % 10;
       v /= 10;
     }
-    e->rdb_n = 0;
+    e->rdb_gen++;
     return B200SR_OK;
   }
   if (!strcmp(key, "rdb_stats")) {
@@ -1067,6 +1307,27 @@ int b200sr_set_option(b200sr_engine* e, const char* key, int value) {
   }
   if (!strcmp(key, "fold_up")) {
     e->opt_fold_up = value;
+    return B200SR_OK;
+  }
+  if (!strcmp(key, "lanes")) {   // host-buffer lanes (streams + workspaces); takes effect for lanes not yet created
+    if (value < 1 || value > 8) return fail(e, B200SR_ERR_INVALID, "lanes must be 1..8");
+    std::lock_guard<std::mutex> g(e->mu);
+    for (auto& l : e->lanes)
+      if (l->busy) return B200SR_ERR_STATE;
+    cudaSetDevice(e->device);
+    while (static_cast<int>(e->lanes.size()) > value) {
+      free_lane(e->lanes.back().get());
+      e->lanes.pop_back();
+    }
+    e->opt_lanes = value;
+    return B200SR_OK;
+  }
+  if (!strcmp(key, "host_chunk")) {   // frames per lane job of a host-buffer call (0 = auto)
+    e->opt_host_chunk = value;
+    return B200SR_OK;
+  }
+  if (!strcmp(key, "ws_limit_mb")) {   // tests: refuse larger workspaces with B200SR_ERR_OOM
+    e->opt_ws_limit_mb = value;
     return B200SR_OK;
   }
   if (!strcmp(key, "profile")) {  // 1: time every launch with CUDA events; read back with b200sr_get_profile
@@ -1108,13 +1369,13 @@ int b200sr_debug_rdb_stats(b200sr_engine* e, long long* out, int max_ctas) {
 // Dev tool: per-item timestamps of the traced fused-RDB launch; [nitems][10] long long.  Returns nitems.
 int b200sr_debug_rdb_trace(b200sr_engine* e, long long* out, int max_items) {
   if (!e || !e->d_rdb_trace) return -1;
-  const int n = std::min(std::abs(max_items), e->rdb_nitems);
+  const int n = std::min(std::abs(max_items), e->stats_nitems);
   if (max_items < 0) {   // negative count: fetch the per-row trace ([nitems][16][3]) instead
     if (out && cudaMemcpy(out, e->d_rdb_trace2, static_cast<size_t>(n) * 48 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    return e->rdb_nitems;
+    return e->stats_nitems;
   }
   if (out && cudaMemcpy(out, e->d_rdb_trace, static_cast<size_t>(n) * 10 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  return e->rdb_nitems;
+  return e->stats_nitems;
 }
 
 // ---- test hooks that need no GPU ----------------------------------------------------------------
@@ -1231,7 +1492,8 @@ int b200sr_debug_conv3x3(int device, const void* in_dev, int n, int h, int w, in
       a.prelu = d_prelu;
     }
     ConvIO io{in_dev, in_pitch, n, h, w};
-    int r = launch_conv(&e, l, epi == 1 ? EPI_PRELU_BF16 : EPI_ACT_BF16, io, a, st);
+    Lane lane;
+    int r = launch_conv(&e, &lane, l, epi == 1 ? EPI_PRELU_BF16 : EPI_ACT_BF16, io, a, st);
     if (r) return r;
     CUDA_TRY(&e, cudaStreamSynchronize(st));
     return B200SR_OK;

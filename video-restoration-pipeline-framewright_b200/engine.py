@@ -8,7 +8,10 @@ used only for device memory and streams; all arithmetic runs in libb200sr.so.
 from __future__ import annotations
 
 import ctypes
-from typing import Dict, Optional, Union
+import os
+import threading
+import weakref
+from typing import Dict, List, Optional, Tuple, Union
 
 import numpy as np
 import torch
@@ -26,12 +29,73 @@ class EngineOutOfMemory(EngineError):
     /root/reference/src/framewright/restorer.py:1746)."""
 
 
+class PinnedPool:
+    """Recycling pool of page-locked host buffers (C ABI b200sr_host_alloc) behind numpy arrays.
+
+    `enhance` returns a fresh ndarray per frame (44 MB at 720p x4).  Allocating it here lets the D2H copy land in
+    the returned array itself -- no pinned -> pageable memcpy (~5 ms per 720p frame) -- and cudaHostAlloc (slow) is
+    paid once per buffer: when the last view of an array dies, its buffer goes back to the pool.  The pool holds at
+    most $B200SR_PINNED_POOL_MB (default 4096) of idle buffers; beyond that, or if pinning fails, buffers are freed /
+    the array is ordinary pageable memory (the engine then stages through its own pinned buffers)."""
+
+    def __init__(self):
+        self._free: Dict[int, List[int]] = {}
+        self._idle_bytes = 0
+        self._lock = threading.Lock()
+        self.cap_bytes = int(os.environ.get("B200SR_PINNED_POOL_MB", "4096")) << 20
+        self.enabled = os.environ.get("B200SR_PINNED_POOL", "1") != "0"
+
+    def _release(self, ptr: int, nbytes: int) -> None:
+        with self._lock:
+            if self._idle_bytes + nbytes <= self.cap_bytes:
+                self._free.setdefault(nbytes, []).append(ptr)
+                self._idle_bytes += nbytes
+                return
+        try:
+            _native.load().b200sr_host_free(ctypes.c_void_p(ptr))
+        except Exception:  # pragma: no cover - interpreter shutdown
+            pass
+
+    def empty(self, shape: Tuple[int, ...], dtype) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        if not self.enabled or nbytes < (1 << 16):
+            return np.empty(shape, dtype=dtype)
+        ptr = None
+        with self._lock:
+            lst = self._free.get(nbytes)
+            if lst:
+                ptr = lst.pop()
+                self._idle_bytes -= nbytes
+        if ptr is None:
+            ptr = _native.load().b200sr_host_alloc(nbytes)
+            if not ptr:
+                return np.empty(shape, dtype=dtype)
+        buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
+        weakref.finalize(buf, self._release, int(ptr), nbytes)
+        return np.frombuffer(buf, dtype=np.uint8, count=nbytes).view(dtype).reshape(shape)
+
+    def trim(self) -> None:
+        """Free every idle buffer (clear_upsampler_cache)."""
+        with self._lock:
+            ptrs = [p for lst in self._free.values() for p in lst]
+            self._free.clear()
+            self._idle_bytes = 0
+        lib = _native.load()
+        for p in ptrs:
+            lib.b200sr_host_free(ctypes.c_void_p(p))
+
+
+PINNED_POOL = PinnedPool()
+
+
 def _fptr(t: torch.Tensor):
     return ctypes.cast(t.data_ptr(), ctypes.POINTER(ctypes.c_float))
 
 
 class B200Engine:
-    """One network on one B200.  Not thread-safe: guard with a lock or use one engine per thread."""
+    """One network on one B200.  `upscale_host` is thread-safe (the C ABI gives every call its own lanes);
+    `upscale_device` calls must be stream-ordered with each other; weight loading / options / close need it idle."""
 
     def __init__(self, model_name_or_arch: Union[str, ArchDesc], state_dict: Dict[str, torch.Tensor], gpu_id: int = 0):
         arch = MODEL_ARCHS[model_name_or_arch] if isinstance(model_name_or_arch, str) else model_name_or_arch
@@ -120,7 +184,7 @@ class B200Engine:
     def upscale_host(self, frames: np.ndarray, out: Optional[np.ndarray] = None, tile: int = 0, tile_pad: int = 10,
                      pre_pad: int = 0) -> np.ndarray:
         """frames: host uint8 (or uint16) [N,H,W,3] or [H,W,3] BGR -> host array of the same dtype, through the C ABI's
-        host-buffer call (H2D + forward + D2H + sync inside)."""
+        host-buffer call (pipelined H2D + forward + D2H inside; the result array is page-locked, `PinnedPool`)."""
         single = frames.ndim == 3
         f = np.ascontiguousarray(frames[None] if single else frames)
         if f.dtype not in (np.uint8, np.uint16) or f.ndim != 4 or f.shape[-1] != 3:
@@ -128,7 +192,7 @@ class B200Engine:
         n, h, w, _ = f.shape
         s = self.scale
         if out is None:
-            out = np.empty((n, h * s, w * s, 3), dtype=f.dtype)
+            out = PINNED_POOL.empty((n, h * s, w * s, 3), f.dtype)
         elif out.dtype != f.dtype or tuple(out.shape) != (n, h * s, w * s, 3) or not out.flags["C_CONTIGUOUS"]:
             raise EngineError("bad output array")
         fn = self._lib.b200sr_upscale_host_u16 if f.dtype == np.uint16 else self._lib.b200sr_upscale_host_u8

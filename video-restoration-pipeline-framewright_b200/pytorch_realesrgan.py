@@ -106,7 +106,9 @@ def is_pytorch_esrgan_available() -> bool:
 def _local_weights(model_name: str) -> Optional[str]:
     import os
 
-    for d in (os.environ.get("B200SR_WEIGHTS_DIR"), "weights", "."):
+    from .upsampler import weights_dir
+
+    for d in (weights_dir(), "weights", "."):
         if d:
             p = os.path.join(d, model_name + ".pth")
             if os.path.isfile(p):
@@ -249,6 +251,10 @@ def clear_upsampler_cache():
     if had:
         try:
             import torch
+
+            from .engine import PINNED_POOL
+
+            PINNED_POOL.trim()
             if torch.cuda.is_available():
                 torch.cuda.empty_cache()
         except ImportError:

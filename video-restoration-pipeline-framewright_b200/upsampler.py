@@ -7,9 +7,15 @@ The reference builds `RealESRGANer(scale, model_path, dni_weight, model, tile, t
 constructor and that call; the pre-process / tile loop / forward / post-process / uint8 conversion all
 run on the GPU inside libb200sr.so (`b200sr_upscale_host_u8`).
 
-Unlike the upstream object this one is re-entrant: `enhance` keeps no per-call state on `self` and
-serialises engine access with a lock (the reference calls it from several threads,
-`restorer.py:1894`).
+Unlike the upstream object this one is re-entrant: `enhance` keeps no per-call state on `self`, and the engine's
+host-buffer call is thread-safe (each call takes one of the engine's lanes: own stream, workspace and pinned
+staging, csrc/b200sr.cu), so the `parallel_frames` threads of the reference (`restorer.py:1894`) overlap their
+copies with each other's kernels.  `close()` waits for calls in flight; a closed upsampler raises `EngineError`.
+
+Weights: a local checkpoint file is loaded as upstream does (params_ema | params, strict).  A URL is downloaded
+into the weights directory like upstream's `load_file_from_url`; when that is impossible the constructor RAISES
+(`FileNotFoundError`) -- it never falls back to random weights silently.  Synthetic weights (benchmarks, tests)
+must be asked for explicitly: `synthetic_seed=<int>`, `state_dict=...` or `B200SR_SYNTHETIC_WEIGHTS=<seed>`.
 """
 from __future__ import annotations
 
@@ -62,6 +68,50 @@ def _load_checkpoint(path: str) -> Dict[str, torch.Tensor]:
     return loadnet
 
 
+def weights_dir() -> str:
+    """Where downloaded / user-provided checkpoints live: $B200SR_WEIGHTS_DIR or <package>/weights."""
+    return os.environ.get("B200SR_WEIGHTS_DIR") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "weights")
+
+
+def _resolve_checkpoint(model_path: str) -> str:
+    """Local file -> itself; URL -> cached copy in weights_dir(), downloaded if missing (upstream
+    `load_file_from_url`).  Raises FileNotFoundError when neither is possible (offline hosts)."""
+    mp = str(model_path)
+    if os.path.isfile(mp):
+        return mp
+    if mp.startswith(("http://", "https://")):
+        fname = os.path.basename(mp.split("?")[0])
+        for d in (weights_dir(), "weights", "."):
+            cand = os.path.join(d, fname)
+            if os.path.isfile(cand):
+                return cand
+        dst = os.path.join(weights_dir(), fname)
+        try:
+            import urllib.request
+
+            os.makedirs(weights_dir(), exist_ok=True)
+            tmp = dst + ".part"
+            with urllib.request.urlopen(mp, timeout=float(os.environ.get("B200SR_DOWNLOAD_TIMEOUT", "20"))) as r, \
+                    open(tmp, "wb") as f:
+                while True:
+                    chunk = r.read(1 << 20)
+                    if not chunk:
+                        break
+                    f.write(chunk)
+            os.replace(tmp, dst)
+            return dst
+        except Exception as exc:
+            raise FileNotFoundError(
+                f"model weights {fname} are not available: download of {mp} failed ({exc}); "
+                f"place the file in {weights_dir()} (or set B200SR_WEIGHTS_DIR)") from exc
+    # a bare / relative file name (face_restore.py:391 passes 'RealESRGAN_x4plus.pth'): look in the weights directories
+    for d in (weights_dir(), "weights"):
+        cand = os.path.join(d, os.path.basename(mp))
+        if os.path.isfile(cand):
+            return cand
+    raise FileNotFoundError(f"model weights not found: {mp} (also looked in {weights_dir()})")
+
+
 def _arch_for_model_path(model_path: Optional[str]) -> Optional[str]:
     if not model_path:
         return None
@@ -74,7 +124,7 @@ class RealESRGANer:
     """Drop-in for `realesrgan.RealESRGANer` on a B200."""
 
     def __init__(self, scale, model_path=None, dni_weight=None, model=None, tile=0, tile_pad=10, pre_pad=10,
-                 half=False, device=None, gpu_id=None, state_dict=None, model_name=None, synthetic_seed=0):
+                 half=False, device=None, gpu_id=None, state_dict=None, model_name=None, synthetic_seed=None):
         self.scale = int(scale)
         self.tile_size = int(tile or 0)
         self.tile_pad = int(tile_pad)
@@ -120,19 +170,23 @@ class RealESRGANer:
         if dni_pair is not None:
             state_dict = self.dni(dni_pair[0], dni_pair[1], dni_weight)
         if state_dict is None:
-            local = str(model_path) if model_path and os.path.isfile(str(model_path)) else None
-            if local is not None:
-                state_dict = _load_checkpoint(local)
-            else:
-                # Weight URLs cannot be fetched offline: deterministic synthetic weights of the same architecture.
-                if model_path:
-                    logger.warning("checkpoint %s not available locally; using synthetic weights (seed %d)",
-                                   model_path, synthetic_seed)
+            if synthetic_seed is None and os.environ.get("B200SR_SYNTHETIC_WEIGHTS", "") != "":
+                synthetic_seed = int(os.environ["B200SR_SYNTHETIC_WEIGHTS"])
+            if synthetic_seed is not None:
+                # explicit opt-in only (benchmarks / tests): deterministic random-init weights of this architecture
                 synth_name = name if name in MODEL_ARCHS else next(k for k, v in MODEL_ARCHS.items() if v == arch)
-                state_dict = make_synthetic_state_dict(synth_name, synthetic_seed)
+                logger.warning("using SYNTHETIC weights (seed %d) for %s: output is not a trained model's",
+                               int(synthetic_seed), synth_name)
+                state_dict = make_synthetic_state_dict(synth_name, int(synthetic_seed))
+            elif model_path:
+                state_dict = _load_checkpoint(_resolve_checkpoint(str(model_path)))   # raises FileNotFoundError
+            else:
+                raise FileNotFoundError("no weights: pass model_path=<file or URL>, state_dict=, or synthetic_seed=")
         self.arch = arch
         self._engine = B200Engine(arch, state_dict, gpu_id=self.gpu_id)
-        self._lock = threading.Lock()
+        self._cv = threading.Condition()
+        self._inflight = 0
+        self._closed = False
 
     @staticmethod
     def dni(net_a: Dict[str, torch.Tensor], net_b: Dict[str, torch.Tensor], dni_weight, key: str = "params",
@@ -150,10 +204,25 @@ class RealESRGANer:
         return {k: float(dni_weight[0]) * a[k].float() + float(dni_weight[1]) * b[k].float() for k in a}
 
     # --------------------------------------------------------------------------------------------
+    def _enter(self) -> None:
+        with self._cv:
+            if self._closed:
+                raise EngineError("upsampler is closed")
+            self._inflight += 1
+
+    def _exit(self) -> None:
+        with self._cv:
+            self._inflight -= 1
+            if self._inflight == 0:
+                self._cv.notify_all()
+
     def _run_u8(self, img_bgr_u8: np.ndarray) -> np.ndarray:   # uint8 or uint16 samples
-        with self._lock:
+        self._enter()
+        try:
             return self._engine.upscale_host(img_bgr_u8, tile=self.tile_size, tile_pad=self.tile_pad,
                                              pre_pad=self.pre_pad)
+        finally:
+            self._exit()
 
     def enhance(self, img: np.ndarray, outscale: Optional[float] = None,
                 alpha_upsampler: str = "realesrgan") -> Tuple[np.ndarray, str]:
@@ -196,12 +265,18 @@ class RealESRGANer:
 
     def enhance_batch(self, frames: np.ndarray) -> np.ndarray:
         """[N,H,W,3] uint8 BGR -> [N,H*s,W*s,3]; frames are independent (one launch sequence for all N)."""
-        with self._lock:
-            return self._engine.upscale_host(frames, tile=self.tile_size, tile_pad=self.tile_pad, pre_pad=self.pre_pad)
+        return self._run_u8(frames)
 
     @property
     def engine(self) -> B200Engine:
         return self._engine
 
     def close(self) -> None:
+        """Waits for calls in flight (other threads inside `enhance`), then destroys the engine.  Idempotent."""
+        with self._cv:
+            if self._closed:
+                return
+            self._closed = True
+            while self._inflight > 0:
+                self._cv.wait()
         self._engine.close()
