@@ -284,11 +284,14 @@ def run_b200(args):
     pageable = [frames[i % B].copy() for i in range(e2e_frames)]     # ordinary numpy arrays, as cv2.imread returns
 
     def run_enhance(nthreads: int) -> float:
-        outs = [None] * e2e_frames
+        keep = {}                                 # outputs are consumed and dropped, as a caller that writes them out
 
         def work(k):
             for i in range(k, e2e_frames, nthreads):
-                outs[i] = upsampler.enhance(pageable[i], outscale=4)[0]
+                out = upsampler.enhance(pageable[i], outscale=4)[0]
+                if i == 0:
+                    keep[0] = out
+                del out
 
         barrier()
         t0 = time.perf_counter()
@@ -302,23 +305,28 @@ def run_b200(args):
                 t.join()
         torch.cuda.synchronize()
         ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-        run_enhance.last = outs
+        run_enhance.last = keep[0]
         return world * e2e_frames / (ms * 1e-3)
 
-    run_enhance(2)                                # warm-up: lanes, pinned pool, workspaces
+    run_enhance(4)                                # warm-up: lanes, pinned result pool, workspaces
     e2e_1t = run_enhance(1)
     e2e_2t = run_enhance(2)
     e2e_4t = run_enhance(4)
-    e2e_frame0 = run_enhance.last[0]
-    plugin.enhance_frames_batch(frames, cfg)
+    e2e_frame0 = run_enhance.last
+    for _ in range(2):                            # warm-up (result buffers of this size enter the pinned pool)
+        batch_out = plugin.enhance_frames_batch(frames, cfg)
+        del batch_out
     barrier()
     nb = max(2, min(args.steps, 6))
     t0 = time.perf_counter()
-    for _ in range(nb):
+    for it in range(nb):
         batch_out = plugin.enhance_frames_batch(frames, cfg)
+        if it < nb - 1:
+            del batch_out
     e2e_batch = world * B * nb / (max_over_ranks((time.perf_counter() - t0) * 1e3) * 1e-3)
     big = np.concatenate([frames] * 4)            # 16 frames in one call: the engine pipelines its own chunks
-    plugin.enhance_frames_batch(big[:8], cfg)
+    big_out = plugin.enhance_frames_batch(big, cfg)
+    del big_out
     barrier()
     t0 = time.perf_counter()
     big_out = plugin.enhance_frames_batch(big, cfg)
@@ -328,11 +336,25 @@ def run_b200(args):
     del big_out, batch_out
 
     # ---- per-kernel-class timing (CUDA events around every launch, separate pass so it cannot perturb `value`)
+    # Sustained: the profiled steps follow warm steps back to back (a single pass after an idle gap would run at
+    # boost clocks and flatter every kernel); the per-class figures are averages over `psteps` steps.
+    psteps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        eng.upscale_device(dev_in, out=dev_out)
     eng.set_option("profile", 1)
-    eng.upscale_device(dev_in, out=dev_out)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(psteps):
+        eng.upscale_device(dev_in, out=dev_out)
+    pe1.record()
     torch.cuda.synchronize()
+    prof_step_ms = pe0.elapsed_time(pe1) / psteps
     prof = eng.get_profile()
     eng.set_option("profile", 0)
+    for v in prof.values():
+        v["ms"] /= psteps
+        v["flops"] /= psteps
+        v["launches"] //= psteps
     peaks = _peaks()
     dom = max((k for k in prof if prof[k]["flops"] > 0), key=lambda k: prof[k]["ms"])
     d = prof[dom]
@@ -371,6 +393,8 @@ def run_b200(args):
                        f"burst figure {peaks['bf16_tflops']})",
         "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
         "share_of_step": d["ms"] / conv_ms,
+        "kernel_ms_per_step": conv_ms, "profiled_step_ms": prof_step_ms,
+        "idle_between_kernels_ms": prof_step_ms - conv_ms,
         "per_class": per_class,
     }
     flops_frame = 2.0 * MODEL_ARCHS[MODEL].macs_per_input_pixel() * H * W

@@ -109,6 +109,7 @@ struct b200sr_engine {
   int opt_max_ctas = 0;     // 0 = one per SM
   // optional per-kernel-class timing (CUDA events around every launch; option "profile")
   int opt_fused_rdb = 1;    // run each RDB as one persistent kernel (L2-resident intermediates)
+  int opt_first_v1 = 0;     // input stage with the one-thread-per-pixel kernel (bit-identical; test / A-B timing)
   int opt_fold_up = 1;      // conv_up1/up2 read the nearest-2x upsampling through the duplicated-pixel TMA view
   int opt_rdb_stats = 0;    // dev: collect per-CTA cycle counters of the k-th fused launch of a forward pass (1-based)
   int rdb_gen = 0;          // bumped when a schedule option changes: lanes rebuild their work lists
@@ -598,14 +599,29 @@ int run_first(b200sr_engine* e, Lane* lane, const Region& R, int s, int H, int W
   a.lo = lo;
   a.f0 = f0;
   a.inrgb = inrgb;
-  dim3 grid((W + 127) / 128, H, R.n);
   ProfScope prof_scope(e, PC_FIRST, 2.0 * 9.0 * l.cin * 64 * static_cast<double>(R.n) * H * W, st);
-  if (l.cin == 3) {
-    const size_t sm = 9 * 3 * 64 * sizeof(float);
-    first_conv_kernel<3><<<grid, 128, sm, st>>>(a);
+  if (e->opt_first_v1) {   // one thread per pixel (round-1 kernel; kept for the bit-equality test)
+    dim3 grid((W + 127) / 128, H, R.n);
+    if (l.cin == 3) {
+      const size_t sm = 9 * 3 * 64 * sizeof(float);
+      first_conv_kernel<3><<<grid, 128, sm, st>>>(a);
+    } else {
+      const size_t sm = 9 * 12 * 64 * sizeof(float);
+      first_conv_kernel<12><<<grid, 128, sm, st>>>(a);
+    }
+  } else if (l.cin == 3) {
+    using T = FirstTiled<3>;
+    dim3 grid((W + 127) / 128, (H + T::ROWS - 1) / T::ROWS, R.n);
+    first_conv_tiled_kernel<3><<<grid, 256, T::SMEM_BYTES, st>>>(a);
   } else {
-    const size_t sm = 9 * 12 * 64 * sizeof(float);
-    first_conv_kernel<12><<<grid, 128, sm, st>>>(a);
+    using T = FirstTiled<12>;
+    static bool attr_done[16] = {};
+    if (!attr_done[e->device & 15]) {
+      CUDA_TRY(e, cudaFuncSetAttribute(first_conv_tiled_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+      attr_done[e->device & 15] = true;
+    }
+    dim3 grid((W + 127) / 128, (H + T::ROWS - 1) / T::ROWS, R.n);
+    first_conv_tiled_kernel<12><<<grid, 256, T::SMEM_BYTES, st>>>(a);
   }
   CUDA_TRY(e, cudaGetLastError());
   lane->launches++;
@@ -1303,6 +1319,10 @@ int b200sr_set_option(b200sr_engine* e, const char* key, int value) {
   }
   if (!strcmp(key, "fused_rdb")) {
     e->opt_fused_rdb = value;
+    return B200SR_OK;
+  }
+  if (!strcmp(key, "first_v1")) {
+    e->opt_first_v1 = value;
     return B200SR_OK;
   }
   if (!strcmp(key, "fold_up")) {

@@ -114,6 +114,152 @@ __global__ void __launch_bounds__(128) first_conv_kernel(const FirstArgs a) {
   if (a.inrgb) *reinterpret_cast<float4*>(a.inrgb + pix * 4) = make_float4(centre[0], centre[1], centre[2], 0.f);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// first_conv_tiled_kernel: the same arithmetic (same fp32 FMA order per output value: bias, then taps row-major,
+// input channels innermost -> bit-identical results), laid out for the memory system.  The stage is HBM-bound
+// (3 B in, 448 B out per pixel), so what matters is that every store instruction of a warp writes whole, adjacent
+// lines and that enough loads are in flight:
+//   * a block owns 128 pixels x ROWS rows; the source pixels it needs ((ROWS + 2) x 130, after reflect padding /
+//     pixel-unshuffle / normalisation) are staged ONCE in shared memory as floats, the weights once per block;
+//   * 4 threads per pixel PAIR: thread (pair, g) accumulates channels [16 g, 16 g + 16) of pixels 2 pair, 2 pair + 1,
+//     so a weight vector read from shared memory feeds two pixels, and the four threads of a pixel together write its
+//     whole 128-byte hi line (a warp writes 8 pixel pairs = 2 KB contiguous), 32-byte lo run and fp32 groups.
+template <int CIN>
+struct FirstTiled {
+  static constexpr int ROWS = (CIN == 3) ? 8 : 4;
+  static constexpr int SW_FLOATS = 9 * CIN * 64;
+  static constexpr int SIN_PITCH = 130 * CIN + 2;                       // floats per staged row (+2: bank skew)
+  static constexpr int SMEM_BYTES = (SW_FLOATS + (ROWS + 2) * SIN_PITCH + 128) * 4;
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(256) first_conv_tiled_kernel(const FirstArgs a) {
+  using T = FirstTiled<CIN>;
+  constexpr int S = (CIN == 3) ? 1 : 2;
+  extern __shared__ __align__(16) float s_dyn[];
+  float* s_w = s_dyn;                      // [9][CIN][64]
+  float* s_b = s_dyn + T::SW_FLOATS;       // [64]
+  float* s_p = s_b + 64;                   // [64]
+  float* s_in = s_p + 64;                  // [ROWS + 2][130][CIN] (row pitch SIN_PITCH)
+  const int tx0 = blockIdx.x * 128, y0 = blockIdx.y * T::ROWS, n = blockIdx.z;
+  for (int i = threadIdx.x * 4; i < T::SW_FLOATS; i += 256 * 4)
+    *reinterpret_cast<float4*>(s_w + i) = *reinterpret_cast<const float4*>(a.w + i);
+  if (threadIdx.x < 64) {
+    s_b[threadIdx.x] = a.bias[threadIdx.x];
+    s_p[threadIdx.x] = a.prelu ? a.prelu[threadIdx.x] : 1.f;
+  }
+  // stage the inputs: conv-domain pixel (y0 - 1 + r, tx0 - 1 + px), zero outside the region (conv zero padding)
+  const size_t img = static_cast<size_t>(n) * a.Hs * a.Ws * 3;
+  for (int i = threadIdx.x; i < (T::ROWS + 2) * 130 * S * S; i += 256) {
+    const int sub = i % (S * S);
+    const int px = (i / (S * S)) % 130;
+    const int r = i / (S * S * 130);
+    const int yy = y0 - 1 + r, xx = tx0 - 1 + px;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
+      const int sy = reflect_src(a.oy + yy * S + sub / S, a.Hs, a.H1);
+      const int sx = reflect_src(a.ox + xx * S + sub % S, a.Ws, a.W1);
+      const size_t p = img + (static_cast<size_t>(sy) * a.Ws + sx) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)   // BGR -> RGB, img / max_range as upstream's pre_process
+        v[c] = a.src16 ? static_cast<float>(reinterpret_cast<const uint16_t*>(a.src)[p + 2 - c]) / 65535.0f
+                       : static_cast<float>(a.src[p + 2 - c]) / 255.0f;
+    }
+    float* d = s_in + r * T::SIN_PITCH + px * CIN;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) d[c * S * S + sub] = v[c];
+  }
+  __syncthreads();
+  const int g = threadIdx.x & 3;            // channel group: channels [16 g, 16 g + 16)
+  const int pair = threadIdx.x >> 2;        // pixels tx0 + 2 pair, + 1
+  const int xl = 2 * pair;                  // tile-local x of the first pixel
+  const float* wg = s_w + g * 16;
+#pragma unroll 1
+  for (int r = 0; r < T::ROWS; ++r) {
+    const int y = y0 + r;
+    if (y >= a.H) break;
+    float acc[2][16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[0][c] = acc[1][c] = s_b[g * 16 + c];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const float* row = s_in + (r + ky) * T::SIN_PITCH + xl * CIN;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float v0 = row[kx * CIN + ci], v1 = row[(kx + 1) * CIN + ci];
+          const float* wt = wg + ((ky * 3 + kx) * CIN + ci) * 64;
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wt + c4 * 4);
+            acc[0][c4 * 4 + 0] = fmaf(v0, w4.x, acc[0][c4 * 4 + 0]);
+            acc[0][c4 * 4 + 1] = fmaf(v0, w4.y, acc[0][c4 * 4 + 1]);
+            acc[0][c4 * 4 + 2] = fmaf(v0, w4.z, acc[0][c4 * 4 + 2]);
+            acc[0][c4 * 4 + 3] = fmaf(v0, w4.w, acc[0][c4 * 4 + 3]);
+            acc[1][c4 * 4 + 0] = fmaf(v1, w4.x, acc[1][c4 * 4 + 0]);
+            acc[1][c4 * 4 + 1] = fmaf(v1, w4.y, acc[1][c4 * 4 + 1]);
+            acc[1][c4 * 4 + 2] = fmaf(v1, w4.z, acc[1][c4 * 4 + 2]);
+            acc[1][c4 * 4 + 3] = fmaf(v1, w4.w, acc[1][c4 * 4 + 3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int x = tx0 + xl + j;
+      if (x >= a.W) continue;
+      float (&v)[16] = acc[j];
+      if (a.prelu) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = v[c] > 0.f ? v[c] : v[c] * s_p[g * 16 + c];
+      }
+      const size_t pix = (static_cast<size_t>(n) * a.H + y) * a.W + x;
+      __nv_bfloat16* o = a.out + pix * a.out_pitch + g * 16;
+      uint32_t p[8];
+      if (a.lo) {   // residual-stream pair: bf16 hi + e5m2 lo of the rounding residual (store_trunk_pair's split)
+        float res[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          p[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          res[2 * i] = v[2 * i] - bf16lo_f32(p[i]);
+          res[2 * i + 1] = v[2 * i + 1] - bf16hi_f32(p[i]);
+        }
+        st_global_256(o, p);
+        uint4 l;
+        l.x = f32x4_e5m2(res[0], res[1], res[2], res[3]);
+        l.y = f32x4_e5m2(res[4], res[5], res[6], res[7]);
+        l.z = f32x4_e5m2(res[8], res[9], res[10], res[11]);
+        l.w = f32x4_e5m2(res[12], res[13], res[14], res[15]);
+        *reinterpret_cast<uint4*>(a.lo + lo_off(n, y, x, a.H, a.W) + (g >> 1) * LO_GSTRIDE + (g & 1) * 16) = l;
+      } else {
+        if (a.out_fp16) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) p[i] = pack_f16x2(v[2 * i], v[2 * i + 1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) p[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        }
+        st_global_256(o, p);
+      }
+      if (a.f0) {
+        float* d = a.f0 + trunk_off(n, y, x, a.H, a.W) + static_cast<size_t>(g * 2) * TRUNK_GSTRIDE;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t q[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) q[i] = __float_as_uint(v[h * 8 + i]);
+          st_global_256(d + h * TRUNK_GSTRIDE, q);
+        }
+      }
+      if (a.inrgb && g == 0) {
+        const float* c = s_in + (r + 1) * T::SIN_PITCH + (xl + j + 1) * CIN;   // centre tap (S == 1 only)
+        *reinterpret_cast<float4*>(a.inrgb + pix * 4) = make_float4(c[0], c[CIN > 1 ? 1 : 0], c[CIN > 2 ? 2 : 0], 0.f);
+      }
+    }
+  }
+}
+
 // out[n][Y][X][:] = in[n][Y/2][X/2][:], 64 bf16 channels (F.interpolate(scale_factor=2, mode='nearest')).
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N,
                                                           int H, int W) {
