@@ -43,12 +43,13 @@ H, W = 720, 1280
 METRIC = "frames_per_sec_rrdbnet_x4_720p"
 UNIT = "frames/s"
 BAND = 96      # rows of a 720p frame per step of the CPU reference arm
+STREAMS = 2    # set from --streams
 
 
 def workload_config(B: int, world: int) -> dict:
     return {"workload": f"{MODEL} x4 on {B} synthetic 1280x720 uint8 frames per step per GPU, untiled, "
                         "random-init weights (seed 0)",
-            "frames_per_step_per_gpu": B,
+            "frames_per_step_per_gpu": B, "streams": STREAMS,
             "l2": "per-step working set (>5 GB of activations) exceeds the 126 MB L2",
             "parallelism": f"frame-sharded x{world}, no collective on the data path (process group: timing barrier only)"}
 
@@ -253,22 +254,39 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident throughput (`value`)
-    for _ in range(args.warmup):
-        eng.upscale_device(dev_in, out=dev_out)
+    # ---- device-resident throughput (`value`): K steps alternating between two CUDA streams (every stream has its
+    # own engine lane), so the tail of one step's persistent kernels overlaps the head of the next step's
+    streams = [torch.cuda.Stream() for _ in range(max(1, args.streams))]
+    dev_outs = [dev_out] + [torch.empty_like(dev_out) for _ in streams[1:]]
+    main = torch.cuda.current_stream()
+
+    def run_steps(k: int) -> None:
+        for s in streams:
+            s.wait_stream(main)
+        for i in range(k):
+            j = i % len(streams)
+            with torch.cuda.stream(streams[j]):
+                eng.upscale_device(dev_in, out=dev_outs[j])
+        for s in streams:
+            main.wait_stream(s)
+
+    run_steps(max(args.warmup, len(streams)))
     launches_per_step = eng.last_launch_count
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
-        ev0.record()
-        for _ in range(args.steps):
-            eng.upscale_device(dev_in, out=dev_out)
-        ev1.record()
+        ev0.record(main)
+        run_steps(args.steps)
+        ev1.record(main)
         barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     ms_step = ms_total / args.steps
     fps = world * B * args.steps / (ms_total * 1e-3)
-    timed_frame0 = dev_out[0].cpu().numpy()       # frame 0 of the timed output (parity check below)
+    timed_frame0 = dev_outs[(args.steps - 1) % len(streams)][0].cpu().numpy()   # frame 0 of the last timed step
+    for o in dev_outs[1:]:
+        assert torch.equal(o, dev_out)
+    del dev_outs[1:]
+    torch.cuda.empty_cache()
 
     # ---- device-resident, one frame per call
     one_in, one_out = dev_in[:1].contiguous(), dev_out[:1]
@@ -458,12 +476,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4, help="720p frames per step per GPU")
+    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the timed steps alternate between")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="step", choices=["step", "clip2000"])
     ap.add_argument("--clip-frames", type=int, default=2000)
+    ap.add_argument("--clip-batch", type=int, default=2, help="frames per engine call in the scheduler's workers")
+    ap.add_argument("--clip-threads", type=int, default=3, help="runner threads per worker process")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
     args = ap.parse_args()
+    global STREAMS
+    STREAMS = args.streams
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "clip2000":

@@ -99,7 +99,8 @@ struct b200sr_engine {
   // lanes: `dev_lane` serves the device-pointer entry points (caller's stream), `lanes` the host-buffer ones
   std::mutex mu;                   // lane acquisition, err, prof
   std::condition_variable cv;
-  Lane dev_lane;
+  Lane dev_lane;                                   // device-pointer calls on any stream beyond the first few
+  std::vector<std::pair<cudaStream_t, std::unique_ptr<Lane>>> dev_lanes;   // one lane per caller stream (<= 4)
   std::vector<std::unique_ptr<Lane>> lanes;
   int opt_lanes = 2;
   int opt_host_chunk = 0;          // frames per lane job of a host-buffer call (0 = auto)
@@ -391,7 +392,7 @@ int ensure_ws(b200sr_engine* e, Lane* lane, size_t bytes, cudaStream_t st) {
                                        " MiB workspace exceeds the configured limit (option ws_limit_mb)");
   if (lane->ws) {
     CUDA_TRY(e, cudaStreamSynchronize(st));
-    if (lane == &e->dev_lane) CUDA_TRY(e, cudaDeviceSynchronize());   // earlier enqueues may sit on other streams
+    if (lane->id <= 0) CUDA_TRY(e, cudaDeviceSynchronize());   // device lanes: earlier enqueues may sit on other streams
     cudaFree(lane->ws);
     lane->ws = nullptr;
     lane->ws_bytes = 0;
@@ -951,6 +952,10 @@ void b200sr_destroy(b200sr_engine* e) {
   for (auto* p : e->prelu_dev)
     if (p) cudaFree(p);
   free_lane(&e->dev_lane);
+  for (auto& p : e->dev_lanes) {
+    p.second->stream = nullptr;   // the caller's stream, not ours
+    free_lane(p.second.get());
+  }
   for (auto& l : e->lanes) free_lane(l.get());
   if (e->d_rdb_stats) cudaFree(e->d_rdb_stats);
   if (e->d_rdb_trace) cudaFree(e->d_rdb_trace);
@@ -1081,18 +1086,35 @@ static int enqueue_impl(b200sr_engine* e, Lane* lane, const void* src_dev_v, voi
   return B200SR_OK;
 }
 
-// Device-pointer entry points: asynchronous on the caller's stream, on the engine's device lane.  Calls on one
-// engine must be ordered with each other by the caller (same stream, or events), as with any stream-ordered API.
+// Device-pointer entry points: asynchronous on the caller's stream.  Every caller stream (up to 4) gets its own lane
+// (workspace + work list), so work queued on two streams overlaps -- the tail of one stream's persistent kernels
+// with the head of the other's -- without sharing scratch memory.  Calls on the SAME stream are ordered by the
+// stream; further streams share `dev_lane` and must be ordered with each other by the caller.
+static Lane* device_lane_for(b200sr_engine* e, void* cuda_stream) {
+  std::lock_guard<std::mutex> g(e->mu);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  for (auto& p : e->dev_lanes)
+    if (p.first == st) return p.second.get();
+  if (e->dev_lanes.size() < 4) {
+    e->dev_lanes.emplace_back(st, std::unique_ptr<Lane>(new Lane()));
+    e->dev_lanes.back().second->id = -1 - static_cast<int>(e->dev_lanes.size());
+    return e->dev_lanes.back().second.get();
+  }
+  return &e->dev_lane;
+}
+
 int b200sr_enqueue_u8(b200sr_engine* e, const uint8_t* src_dev, uint8_t* dst_dev, int n, int h, int w, int tile,
                       int tile_pad, int pre_pad, void* cuda_stream) {
   if (!e) return B200SR_ERR_INVALID;
-  return enqueue_impl(e, &e->dev_lane, src_dev, dst_dev, n, h, w, tile, tile_pad, pre_pad, cuda_stream, 0);
+  return enqueue_impl(e, device_lane_for(e, cuda_stream), src_dev, dst_dev, n, h, w, tile, tile_pad, pre_pad,
+                      cuda_stream, 0);
 }
 
 int b200sr_enqueue_u16(b200sr_engine* e, const uint16_t* src_dev, uint16_t* dst_dev, int n, int h, int w, int tile,
                        int tile_pad, int pre_pad, void* cuda_stream) {
   if (!e) return B200SR_ERR_INVALID;
-  return enqueue_impl(e, &e->dev_lane, src_dev, dst_dev, n, h, w, tile, tile_pad, pre_pad, cuda_stream, 1);
+  return enqueue_impl(e, device_lane_for(e, cuda_stream), src_dev, dst_dev, n, h, w, tile, tile_pad, pre_pad,
+                      cuda_stream, 1);
 }
 
 // ---- host-buffer entry point: pipelined over the engine's lanes ---------------------------------------------------

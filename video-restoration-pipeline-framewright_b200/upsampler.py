@@ -216,10 +216,10 @@ class RealESRGANer:
             if self._inflight == 0:
                 self._cv.notify_all()
 
-    def _run_u8(self, img_bgr_u8: np.ndarray) -> np.ndarray:   # uint8 or uint16 samples
+    def _run_u8(self, img_bgr_u8: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:   # uint8 / uint16
         self._enter()
         try:
-            return self._engine.upscale_host(img_bgr_u8, tile=self.tile_size, tile_pad=self.tile_pad,
+            return self._engine.upscale_host(img_bgr_u8, out=out, tile=self.tile_size, tile_pad=self.tile_pad,
                                              pre_pad=self.pre_pad)
         finally:
             self._exit()
@@ -263,9 +263,11 @@ class RealESRGANer:
                                 interpolation=cv2.INTER_LANCZOS4)
         return output, img_mode
 
-    def enhance_batch(self, frames: np.ndarray) -> np.ndarray:
-        """[N,H,W,3] uint8 BGR -> [N,H*s,W*s,3]; frames are independent (one launch sequence for all N)."""
-        return self._run_u8(frames)
+    def enhance_batch(self, frames: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """[N,H,W,3] uint8 BGR -> [N,H*s,W*s,3]; frames are independent.  The engine cuts large batches into lane
+        jobs and pipelines them (copies of one job under the kernels of the other).  `out`: optional destination
+        (page-locked memory is written directly by the D2H copy)."""
+        return self._run_u8(frames, out)
 
     @property
     def engine(self) -> B200Engine:
