@@ -55,7 +55,7 @@ def test_reference_processor_calls_shim(ref_modules, tmp_path, monkeypatch):
             name = next(k for k, v in up_mod.MODEL_ARCHS.items() if v == arch)
             self.name, self.sd = name, state_dict
 
-        def upscale_host(self, frames, tile=0, tile_pad=10, pre_pad=0):
+        def upscale_host(self, frames, out=None, tile=0, tile_pad=10, pre_pad=0):
             created["tile"] = (tile, tile_pad, pre_pad)
             return oracle.make_upsampler(self.name, self.sd, tile=tile, tile_pad=tile_pad, pre_pad=pre_pad).enhance(frames)[0]
 
