@@ -155,29 +155,85 @@ def test_sr_config_validation():
         srm.SRConfig(quality_preset="ultra")
 
 
-def test_sr_backend_dir_api_collects_failures(tmp_path, monkeypatch):
-    """frames-dir in/out: sorted *.png, same names, failures -> warnings 'Frame <name>: <err>', never raises."""
-    (tmp_path / "in").mkdir()
-    for i in range(3):
-        _write_png(tmp_path / "in" / f"frame_{i:08d}.png")
-    calls = []
+class _BatchUpsampler:
+    """Stand-in for the B200 upsampler: x4 nearest, counts calls, can fail on a marker pixel value."""
+    scale = 4
 
-    def fake(inp, outp, cfg):
-        calls.append(Path(inp).name)
-        if "00000001" in str(inp):
-            return False, "boom"
-        Path(outp).write_bytes(b"x")
-        return True, None
+    def __init__(self):
+        self.batches, self.singles = [], 0
 
-    monkeypatch.setattr(srm, "enhance_frame_pytorch", fake)
+    def enhance_batch(self, frames, out=None):
+        self.batches.append(len(frames))
+        if (frames[:, 0, 0, 0] == 66).any():
+            raise RuntimeError("boom")
+        return np.repeat(np.repeat(frames, 4, axis=1), 4, axis=2)
+
+    def enhance(self, img, outscale=None):
+        self.singles += 1
+        if img.ndim == 3 and img[0, 0, 0] == 66:
+            raise RuntimeError("boom")
+        out = np.repeat(np.repeat(img, 4, axis=0), 4, axis=1)
+        return out, "RGB"
+
+    def close(self):
+        pass
+
+
+def test_sr_backend_dir_api_batches_and_collects_failures(tmp_path, monkeypatch):
+    """frames-dir in/out: sorted *.png, same names, consecutive same-size frames in one engine call, unreadable /
+    failing frames -> warnings 'Frame <name>: <err>', progress per frame, never raises."""
+    import cv2
+
+    ind = tmp_path / "in"
+    ind.mkdir()
+    for i in range(9):
+        cv2.imwrite(str(ind / f"frame_{i:08d}.png"), np.full((8, 8, 3), 10 * i, np.uint8))
+    cv2.imwrite(str(ind / "frame_00000009.png"), np.full((6, 12, 3), 99, np.uint8))      # another size: own batch
+    (ind / "frame_00000010.png").write_bytes(b"not a png")
+    cv2.imwrite(str(ind / "frame_00000011.png"), np.full((6, 12, 3), 66, np.uint8))      # the engine fails on this one
+    up = _BatchUpsampler()
+    monkeypatch.setattr(srm, "get_upsampler", lambda cfg: up)
     prog = []
-    res = srm.B200RealESRGANBackend().upscale_frames(tmp_path / "in", tmp_path / "out", 4, prog.append)
-    assert calls == sorted(calls) and len(calls) == 3
-    assert (res.frames_processed, res.frames_failed) == (2, 1)
-    assert res.warnings == ["Frame frame_00000001.png: boom"]
-    assert prog[-1] == 1.0 and res.output_dir == tmp_path / "out" and res.backend_used == "realesrgan_x4plus"
+    res = srm.B200RealESRGANBackend().upscale_frames(ind, tmp_path / "out", 4, prog.append)
+    assert (res.frames_processed, res.frames_failed) == (10, 2)
+    assert sorted(res.warnings) == sorted([f"Frame frame_00000010.png: Failed to read image: {ind / 'frame_00000010.png'}",
+                                           "Frame frame_00000011.png: boom"])
+    assert up.batches == [4, 4, 2] and up.singles == 3      # frame 8 alone; the failed pair (9, 11) retried one by one
+    assert len(prog) == 12 and prog == sorted(prog) and prog[-1] == 1.0
+    assert res.output_dir == tmp_path / "out" and res.backend_used == "realesrgan_x4plus" and res.avg_fps > 0
+    for i in range(9):
+        got = cv2.imread(str(tmp_path / "out" / f"frame_{i:08d}.png"))
+        assert got.shape == (32, 32, 3) and int(got[0, 0, 0]) == 10 * i
+    assert not (tmp_path / "out" / "frame_00000011.png").exists()
     empty = srm.B200RealESRGANBackend().upscale_frames(tmp_path / "none", tmp_path / "out2", 4)
     assert empty.warnings == ["No frames found"]
+
+
+def test_super_resolution_facade_selects_falls_back_and_processes_lists(monkeypatch):
+    """`SuperResolution` (reference :1194-1527): auto selection, fallback from a backend that does not exist here,
+    `process(frames: List)` batching runs of same-size frames, `upscale_frame`, factories."""
+    up = _BatchUpsampler()
+    monkeypatch.setattr(srm, "get_upsampler", lambda cfg: up)
+    monkeypatch.setattr(srm, "is_pytorch_esrgan_available", lambda: True)
+    sr = srm.SuperResolution(srm.SRConfig(scale=4, backend="auto"))
+    assert sr.backend.name == "realesrgan_x4" and sr.get_backend_info()["supported_scales"] == [4]
+    assert srm.SuperResolution(srm.SRConfig(scale=4, backend="hat_large", quality_preset="quality")).backend.name \
+        == "realesrgan_x4"                                       # unavailable backend -> the preset's fallback chain
+    assert srm.SuperResolution(srm.SRConfig(backend="realesrgan_anime")).backend._get_model_name() \
+        == "RealESRGAN_x4plus_anime_6B"
+    assert set(sr.get_available_backends()) == {"realesrgan_x2", "realesrgan_x4", "realesrgan_anime",
+                                                "realesrgan_general", "realesrgan_animevideo"}
+    frames = [np.full((4, 6, 3), i, np.uint8) for i in range(5)] + [np.full((3, 3, 3), 7, np.uint8)]
+    outs = sr.process(frames, scale=4)
+    assert [o.shape for o in outs] == [(16, 24, 3)] * 5 + [(12, 12, 3)] and [int(o[0, 0, 0]) for o in outs] == [0, 1, 2, 3, 4, 7]
+    assert up.batches == [5, 1]
+    assert sr.upscale_frame(frames[0]).shape == (16, 24, 3)
+    assert sr.estimate_vram_usage(1280, 720) == 2000 + (1280 * 720 * 3 * 4 * 17) // (1024 * 1024)
+    assert srm.create_super_resolution(scale=2).backend.supported_scales == [2]
+    assert srm.get_recommended_backend() == "realesrgan_x4" and "realesrgan_x4" in srm.list_available_backends()
+    monkeypatch.setattr(srm, "is_pytorch_esrgan_available", lambda: False)
+    with pytest.raises(RuntimeError, match="No super-resolution backend available"):
+        srm.SuperResolution(srm.SRConfig())
 
 
 # ---- frame scheduler (reference tests/test_multi_gpu.py:510-554 restated) -------------------------------

@@ -35,8 +35,14 @@ class SyntheticClip:
     def name(self, i: int) -> str:
         return f"frame_{i + 1:08d}.png"
 
+    _CACHE: dict = {}     # per process: (h, w, seed, pool) -> base frames (a worker serves several jobs)
+
     def open(self) -> None:
         if self._frames is not None:
+            return
+        key = (self.h, self.w, self.seed, self.pool)
+        if key in SyntheticClip._CACHE:
+            self._frames = SyntheticClip._CACHE[key]
             return
         yy, xx = np.mgrid[0:self.h, 0:self.w].astype(np.float32)
         frames = []
@@ -50,7 +56,7 @@ class SyntheticClip:
             img += 0.08 * np.sin(xx[..., None] * 0.9) * np.sin(yy[..., None] * 1.1)
             img += rng.normal(0, 0.04, size=img.shape).astype(np.float32)
             frames.append(np.clip(img * 255.0, 0, 255).round().astype(np.uint8))
-        self._frames = frames
+        self._frames = SyntheticClip._CACHE[key] = frames
 
     def close(self) -> None:
         pass
@@ -86,7 +92,8 @@ def run_clip(args) -> int:
                                batch=args.clip_batch, model_name=model, scale=4, tile=0)
     t_start = time.time()
     try:
-        warm = d.distribute_frames(SyntheticClip(8 * n_gpus, h, w, seed=5), None, None, sink=ChecksumSink())
+        # warm-up job on the same clip (same seed): engines, workspaces, pinned pools and the workers' base frames
+        warm = d.distribute_frames(SyntheticClip(8 * n_gpus, h, w, seed=4), None, None, sink=ChecksumSink())
         assert not warm.errors, warm.errors
         startup_s = time.time() - t_start
         per_frame = []
