@@ -1,0 +1,334 @@
+"""Adapters for the callers either side of the hot path.
+
+f2  `enhance_frames_batched`: what `VideoRestorer.enhance_frames` / `_enhance_frames_sequential` / `_parallel`
+    (`/root/reference/src/framewright/restorer.py:1604-1973`) do around one `enhance_frame_pytorch` call per frame,
+    but handing the WHOLE frame list to the sharded scheduler: resume from the checkpoint, `update_stage("enhance")`,
+    a `CheckpointManager.update_frame(frame_number, input_path, output_path)` and an `_update_progress(...)` per
+    frame AS IT COMPLETES, the out-of-memory tile ladder ("memory" / "vram" in the error -> next smaller tile of
+    `get_adaptive_tile_sequence`), `continue_on_error` (copy the original frame so the video still assembles) and the
+    `ErrorReport` bookkeeping.
+f4  `make_streaming_enhancer` -> the `enhance_fn(List[PipelineFrame]) -> List[PipelineFrame]` that
+    `StreamingPipeline.set_enhancer` takes (`processors/streaming.py:876-885`); `multi_gpu_process_frames` -> the
+    `MultiGPUProcessor.process_frames(frames, process_func, callback)` call shape
+    (`infrastructure/gpu/distributor.py:687-752`) over the scheduler's shared-memory transport.
+f1  `RawVideoReader` / `RawVideoWriter`: raw bgr24 frame pipes (what `ffmpeg -f rawvideo -pix_fmt bgr24 -` produces /
+    consumes) and `upscale_raw_stream`, the decode -> engine -> encode path with no PNG round trip and no per-frame
+    `ffprobe` (`restorer.py:1109-1118, 3001-3027`, `validators.py:165-181`).
+"""
+from __future__ import annotations
+
+import logging
+import shutil
+import time
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Any, BinaryIO, Callable, Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .pytorch_realesrgan import PyTorchESRGANConfig
+from .tile_sizing import get_adaptive_tile_sequence
+
+logger = logging.getLogger(__name__)
+
+
+class EnhancementError(RuntimeError):
+    """Mirror of `framewright.errors.EnhancementError` for callers that do not import the reference package."""
+
+
+def _is_vram_error(msg: Optional[str]) -> bool:
+    return bool(msg) and ("vram" in msg.lower() or "memory" in msg.lower())   # restorer.py:1746
+
+
+def _frame_number(path: Path) -> int:
+    return int(Path(path).stem.split("_")[-1])                                  # restorer.py:1774
+
+
+def enhance_frames_batched(frames: Sequence[Path], enhanced_dir: Path, config: PyTorchESRGANConfig, *,
+                           checkpoint_manager: Any = None, update_progress: Optional[Callable[..., None]] = None,
+                           error_report: Any = None, continue_on_error: bool = True,
+                           frame_resolution: Optional[Tuple[int, int]] = None, tile_sequence: Optional[List[int]] = None,
+                           distributor: Any = None, gpu_ids: Optional[List[int]] = None,
+                           error_cls: type = EnhancementError, **hooks) -> int:
+    """Enhance `frames` (frame_XXXXXXXX.png paths) into `enhanced_dir/<same name>` on all healthy GPUs.
+    Returns the number of frames enhanced (frames replaced by their original under `continue_on_error` count, as in
+    the reference).  `checkpoint_manager`, `update_progress(stage=, progress=, frames_completed=, frames_total=)` and
+    `error_report` (`add_success()` / `add_error(name, exc)`) are the reference's own objects, passed in by the caller."""
+    from .multi_gpu import GPUInfo, LoadBalanceStrategy, MultiGPUDistributor, query_gpus
+
+    frames = [Path(f) for f in frames]
+    if not frames:
+        raise error_cls("No frames found to enhance")
+    total_all = len(frames)
+    if checkpoint_manager is not None:
+        checkpoint = checkpoint_manager.load_checkpoint()
+        if checkpoint and checkpoint.stage == "enhance":
+            frames = checkpoint_manager.get_unprocessed_frames(frames)
+            logger.info(f"Resuming enhancement: {len(frames)} frames remaining")
+    if not frames:
+        logger.info("All frames already enhanced")
+        return total_all
+    enhanced_dir = Path(enhanced_dir)
+    enhanced_dir.mkdir(parents=True, exist_ok=True)
+    if checkpoint_manager is not None:
+        checkpoint_manager.update_stage("enhance")
+    if tile_sequence is None:
+        tile_sequence = get_adaptive_tile_sequence(frame_resolution or (1920, 1080), config.scale_factor,
+                                                   starting_tile_size=config.tile_size or None)
+    total = len(frames)
+    if update_progress:
+        update_progress(stage="enhance_frames", progress=0.0, frames_completed=0, frames_total=total)
+    own = distributor is None
+    if own:
+        gpus = None
+        if gpu_ids is not None:
+            gpus = [g for g in query_gpus() if g.id in gpu_ids] or [GPUInfo(i, f"GPU{i}", 1, 1, 0.0) for i in gpu_ids]
+        distributor = MultiGPUDistributor(gpus=gpus, strategy=LoadBalanceStrategy.ROUND_ROBIN,
+                                          model_name=config.model_name, scale=config.scale_factor,
+                                          tile=config.tile_size, tile_pad=config.tile_pad, pre_pad=config.pre_pad)
+    state = {"completed": 0, "enhanced": 0}
+    try:
+        todo = list(frames)
+        tile_index = 0
+        while todo:
+            vram_failed: List[Path] = []
+            last_err: Dict[str, str] = {}
+
+            def on_frame(i: int, name: str, ok: bool, err: Optional[str], gpu: int, _todo=todo) -> None:
+                src = _todo[i]
+                if not ok and _is_vram_error(err) and tile_index + 1 < len(tile_sequence):
+                    vram_failed.append(src)                 # retried below with the next smaller tile
+                    last_err[src.name] = err or ""
+                    return
+                out = enhanced_dir / src.name
+                if ok:
+                    state["enhanced"] += 1
+                    if error_report is not None:
+                        error_report.add_success()
+                    if checkpoint_manager is not None:
+                        checkpoint_manager.update_frame(frame_number=_frame_number(src), input_path=src, output_path=out)
+                else:
+                    if error_report is not None:
+                        error_report.add_error(src.name, error_cls(err or "Unknown error"))
+                    if not continue_on_error:
+                        state["fatal"] = f"Failed to enhance frame {src.name}: {err}"
+                    else:
+                        try:   # keep the video assemblable: the original frame stands in (restorer.py:1790-1800)
+                            shutil.copy2(src, out)
+                            logger.warning(f"Frame {src.name} enhancement failed, using original. Error: {err}")
+                            state["enhanced"] += 1
+                        except Exception as copy_err:
+                            logger.error(f"Could not copy original frame: {copy_err}")
+                state["completed"] += 1
+                if update_progress:
+                    update_progress(stage="enhance_frames", progress=state["completed"] / total,
+                                    frames_completed=state["completed"], frames_total=total)
+
+            distributor.distribute_frames(todo, None, enhanced_dir, frame_callback=on_frame, **hooks)
+            if state.get("fatal"):
+                raise error_cls(state["fatal"])
+            if not vram_failed:
+                break
+            tile_index += 1
+            new_tile = tile_sequence[tile_index]
+            logger.info(f"VRAM error, reducing tile size to {new_tile}")
+            config.tile_size = new_tile                      # the reference mutates the running tile size the same way
+            distributor._engine_kwargs.update(tile=new_tile)
+            todo = sorted(vram_failed)
+    finally:
+        if own:
+            distributor.close()
+        if checkpoint_manager is not None and hasattr(checkpoint_manager, "force_save"):
+            try:
+                checkpoint_manager.force_save()
+            except Exception:  # pragma: no cover
+                pass
+    if update_progress:
+        update_progress(stage="enhance_frames", progress=1.0, frames_completed=state["completed"],
+                        frames_total=total, eta_seconds=0.0)
+    return state["enhanced"] + (total_all - total)
+
+
+# ------------------------------------------------------------------------------------------------ f4
+def make_streaming_enhancer(config: PyTorchESRGANConfig, load: Optional[Callable[[Path], np.ndarray]] = None,
+                            upsampler: Any = None) -> Callable[[List[Any]], List[Any]]:
+    """`enhance_fn` for `StreamingPipeline.set_enhancer`: takes the pipeline's chunk of `PipelineFrame`s (`.index`,
+    `.path`, `.data`, `.processed`, `.error`), runs every run of same-size frames as one engine batch, and returns the
+    same objects with `.data` replaced by the upscaled frame and `.processed` set."""
+    from .pytorch_realesrgan import get_upsampler
+
+    def _load(p: Path) -> np.ndarray:
+        import cv2
+
+        img = cv2.imread(str(p), cv2.IMREAD_UNCHANGED)
+        if img is None:
+            raise IOError(f"Failed to read image: {p}")
+        return img
+
+    loader = load or _load
+
+    def enhance_fn(frames: List[Any]) -> List[Any]:
+        up = upsampler or get_upsampler(config)
+        imgs: List[Optional[np.ndarray]] = []
+        for f in frames:
+            try:
+                imgs.append(f.data if isinstance(getattr(f, "data", None), np.ndarray) else loader(f.path))
+            except Exception as e:
+                imgs.append(None)
+                f.error = str(e)
+        i = 0
+        while i < len(frames):
+            if imgs[i] is None:
+                i += 1
+                continue
+            j = i + 1
+            plain = imgs[i].ndim == 3 and imgs[i].shape[2] == 3 and imgs[i].dtype == np.uint8
+            while plain and j < len(frames) and imgs[j] is not None and imgs[j].shape == imgs[i].shape \
+                    and imgs[j].dtype == np.uint8 and j - i < 8:
+                j += 1
+            try:
+                if j - i > 1:
+                    outs = up.enhance_batch(np.stack(imgs[i:j]))
+                else:
+                    outs = [up.enhance(imgs[i], outscale=config.scale_factor)[0]]
+                for k in range(i, j):
+                    frames[k].data = outs[k - i]
+                    frames[k].processed = True
+                    frames[k].error = None
+            except Exception as e:
+                for k in range(i, j):
+                    frames[k].error = str(e)
+            i = j
+        return frames
+
+    return enhance_fn
+
+
+@dataclass
+class ProcessingResult:
+    """Mirror of `infrastructure.gpu.distributor.ProcessingResult`."""
+    frame_index: int
+    device_id: int
+    success: bool
+    output: Optional[np.ndarray] = None
+    error: Optional[str] = None
+    elapsed_seconds: float = 0.0
+
+
+def multi_gpu_process_frames(frames: List[np.ndarray], config: PyTorchESRGANConfig, pool: Any = None,
+                             callback: Optional[Callable[[ProcessingResult], None]] = None,
+                             gpu_ids: Optional[List[int]] = None, **hooks) -> List[ProcessingResult]:
+    """`MultiGPUProcessor.process_frames(frames, process_func, callback)` for the upscaling operator: a list of frame
+    arrays in, per-frame `ProcessingResult`s out (sorted by frame index), frames sharded over the GPUs through shared
+    memory (no files).  The reference's `process_func(frame, device_id)` is the engine itself here."""
+    from .multi_gpu import query_gpus
+    from .scheduler import ArraySink, ArraySource, SchedulerPool, SharedArray
+
+    if not frames:
+        return []
+    shape = frames[0].shape
+    if any(f.shape != shape or f.dtype != np.uint8 for f in frames) or len(shape) != 3 or shape[2] != 3:
+        raise ValueError("multi_gpu_process_frames needs same-size uint8 BGR frames")
+    s = int(config.scale_factor)
+    own = pool is None
+    if own:
+        ids = gpu_ids if gpu_ids is not None else [g.id for g in query_gpus()] or [0]
+        pool = SchedulerPool(ids, workers_per_gpu=3)
+    sin = SharedArray((len(frames),) + tuple(shape))
+    sout = SharedArray((len(frames), shape[0] * s, shape[1] * s, 3))
+    results: Dict[int, ProcessingResult] = {}
+    t0 = time.time()
+    try:
+        a = sin.array
+        for i, f in enumerate(frames):
+            a[i] = f
+        cfg = {"model_name": config.model_name, "scale_factor": s, "tile_size": config.tile_size,
+               "tile_pad": config.tile_pad, "pre_pad": config.pre_pad}
+
+        def on_frame(i: int, name: str, ok: bool, err: Optional[str], gpu: int) -> None:
+            r = ProcessingResult(i, gpu, ok, sout.array[i].copy() if ok else None, err, time.time() - t0)
+            results[i] = r
+            if callback:
+                callback(r)
+
+        pool.run(ArraySource(sin), ArraySink(sout), cfg, batch=2, frame_callback=on_frame, **hooks)
+    finally:
+        sin.release()
+        sout.release()
+        if own:
+            pool.close()
+    return [results[i] for i in sorted(results)]
+
+
+# ------------------------------------------------------------------------------------------------ f1
+class RawVideoReader:
+    """Frames from a raw bgr24 byte stream (`ffmpeg -i in.mp4 -f rawvideo -pix_fmt bgr24 -`): width x height x 3 bytes
+    per frame, no container, no per-frame files."""
+
+    def __init__(self, stream: BinaryIO, width: int, height: int):
+        self.stream, self.width, self.height = stream, int(width), int(height)
+        self.frame_bytes = self.width * self.height * 3
+
+    def __iter__(self) -> Iterator[np.ndarray]:
+        while True:
+            buf = bytearray(self.frame_bytes)
+            view, got = memoryview(buf), 0
+            while got < self.frame_bytes:
+                n = self.stream.readinto(view[got:])
+                if not n:
+                    break
+                got += n
+            if got < self.frame_bytes:
+                if got:
+                    logger.warning("raw stream ended inside a frame (%d of %d bytes)", got, self.frame_bytes)
+                return
+            yield np.frombuffer(buf, np.uint8).reshape(self.height, self.width, 3)
+
+
+class RawVideoWriter:
+    """Frames to a raw bgr24 byte stream (`ffmpeg -f rawvideo -pix_fmt bgr24 -s WxH -r fps -i - out.mp4`)."""
+
+    def __init__(self, stream: BinaryIO):
+        self.stream = stream
+        self.frames = 0
+
+    def write(self, frame: np.ndarray) -> None:
+        self.stream.write(memoryview(np.ascontiguousarray(frame)).cast("B"))
+        self.frames += 1
+
+
+def upscale_raw_stream(src: BinaryIO, dst: BinaryIO, width: int, height: int, config: PyTorchESRGANConfig,
+                       num_frames: Optional[int] = None, pool: Any = None, batch: int = 4, upsampler: Any = None,
+                       progress_callback: Optional[Callable[[float, str], None]] = None) -> int:
+    """decode pipe -> engine -> encode pipe, frames in order, bounded memory.  With a `SchedulerPool` (and a known
+    `num_frames`) the frames are spread over its GPUs through the shared-memory ring; otherwise one engine in this
+    process batches them.  Returns the number of frames written."""
+    from .pytorch_realesrgan import get_upsampler
+
+    reader, writer = RawVideoReader(src, width, height), RawVideoWriter(dst)
+    s = int(config.scale_factor)
+    if pool is not None and num_frames:
+        cfg = {"model_name": config.model_name, "scale_factor": s, "tile_size": config.tile_size,
+               "tile_pad": config.tile_pad, "pre_pad": config.pre_pad}
+        pool.stream(iter(reader), cfg, lambda i, out: writer.write(out), num_frames=num_frames,
+                    frame_shape=(height, width), scale=s, batch=2, progress_callback=progress_callback)
+        return writer.frames
+    up = upsampler or get_upsampler(config)
+    chunk: List[np.ndarray] = []
+
+    def flush() -> None:
+        if not chunk:
+            return
+        outs = up.enhance_batch(np.stack(chunk))
+        for o in outs:
+            writer.write(o)
+        chunk.clear()
+        if progress_callback and num_frames:
+            progress_callback(min(1.0, writer.frames / num_frames), f"Processed {writer.frames}/{num_frames} frames")
+
+    for frame in reader:
+        chunk.append(frame)
+        if len(chunk) >= batch:
+            flush()
+    flush()
+    return writer.frames
