@@ -36,6 +36,7 @@ struct Layer {
   std::vector<float> w, b;      // host fp32 OIHW / bias
   uint8_t* d_wpack = nullptr;   // packed bf16 image (tensor-core layers)
   float* d_wfirst = nullptr;    // [9][cin][64] fp32 (first layer, CUDA-core kernel)
+  std::vector<float> wfirst;    // the same on the host (3-channel first layer: passed as a kernel parameter)
   float* d_bias = nullptr;      // coutp floats
 };
 
@@ -110,7 +111,8 @@ struct b200sr_engine {
   int opt_max_ctas = 0;     // 0 = one per SM
   // optional per-kernel-class timing (CUDA events around every launch; option "profile")
   int opt_fused_rdb = 1;    // run each RDB as one persistent kernel (L2-resident intermediates)
-  int opt_first_v1 = 0;     // input stage with the one-thread-per-pixel kernel (bit-identical; test / A-B timing)
+  int opt_first_v1 = 0;     // input stage: 0 = constant-bank kernel (3 ch) / tiled kernel (12 ch); 1 = round-1 per-pixel
+                            // kernel; 2 = tiled kernel for 3 ch too (all bit-identical; tests / A-B timing)
   int opt_fold_up = 1;      // conv_up1/up2 read the nearest-2x upsampling through the duplicated-pixel TMA view
   int opt_rdb_stats = 0;    // dev: collect per-CTA cycle counters of the k-th fused launch of a forward pass (1-based)
   int rdb_gen = 0;          // bumped when a schedule option changes: lanes rebuild their work lists
@@ -601,7 +603,7 @@ int run_first(b200sr_engine* e, Lane* lane, const Region& R, int s, int H, int W
   a.f0 = f0;
   a.inrgb = inrgb;
   ProfScope prof_scope(e, PC_FIRST, 2.0 * 9.0 * l.cin * 64 * static_cast<double>(R.n) * H * W, st);
-  if (e->opt_first_v1) {   // one thread per pixel (round-1 kernel; kept for the bit-equality test)
+  if (e->opt_first_v1 == 1) {   // one thread per pixel, weights in shared memory (round-1 kernel; bit-equality test)
     dim3 grid((W + 127) / 128, H, R.n);
     if (l.cin == 3) {
       const size_t sm = 9 * 3 * 64 * sizeof(float);
@@ -610,6 +612,17 @@ int run_first(b200sr_engine* e, Lane* lane, const Region& R, int s, int H, int W
       const size_t sm = 9 * 12 * 64 * sizeof(float);
       first_conv_kernel<12><<<grid, 128, sm, st>>>(a);
     }
+  } else if (l.cin == 3 && e->opt_first_v1 == 0) {
+    // weights, bias and PReLU slopes as a kernel parameter: every FFMA reads its weight from the constant bank
+    FirstWeights3 cw;
+    memcpy(cw.w, l.wfirst.data(), sizeof(cw.w));
+    for (int c = 0; c < 64; ++c) {
+      cw.b[c] = l.b[c];
+      cw.p[c] = prelu ? e->prelu_host[0][c] : 1.f;
+    }
+    cw.has_prelu = prelu ? 1 : 0;
+    dim3 grid((W + 127) / 128, H, R.n);
+    first_conv3_const_kernel<<<grid, 128, 0, st>>>(a, cw);
   } else if (l.cin == 3) {
     using T = FirstTiled<3>;
     dim3 grid((W + 127) / 128, (H + T::ROWS - 1) / T::ROWS, R.n);
@@ -1012,6 +1025,7 @@ int b200sr_finalize(b200sr_engine* e) {
           for (int t = 0; t < 9; ++t) wf[(static_cast<size_t>(t) * l.cin + ci) * 64 + co] = l.w[(static_cast<size_t>(co) * l.cin + ci) * 9 + t];
       if (!l.d_wfirst) CUDA_TRY(e, cudaMalloc(&l.d_wfirst, wf.size() * 4));
       CUDA_TRY(e, cudaMemcpy(l.d_wfirst, wf.data(), wf.size() * 4, cudaMemcpyHostToDevice));
+      l.wfirst = wf;
     } else {
       std::vector<uint8_t> img = pack_weights(l);
       if (!l.d_wpack) CUDA_TRY(e, cudaMalloc(&l.d_wpack, img.size()));

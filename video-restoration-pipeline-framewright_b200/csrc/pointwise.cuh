@@ -260,6 +260,104 @@ __global__ void __launch_bounds__(256) first_conv_tiled_kernel(const FirstArgs a
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// first_conv3_const_kernel (3 input channels: RRDBNet x4 and SRVGGNetCompact).  ncu on the tiled kernel above showed
+// it bound by SHARED-MEMORY instruction issue (mio_throttle + short_scoreboard: 0.82 wavefronts per cycle per SM for
+// the weight reads), not by HBM.  Here the 27 x 64 weights, the bias and the PReLU slopes travel as a KERNEL PARAMETER
+// (7.4 KB, constant bank 0): with the loops fully unrolled every FFMA takes its weight as a constant-bank operand,
+// so the inner loop is pure FFMA -- no load instructions, no shared memory -- and one thread per pixel keeps its 27
+// input values in registers.  Same fp32 FMA order per output value as the other two kernels -> identical bits.
+struct FirstWeights3 {
+  float w[27][64];     // [(ky * 3 + kx) * 3 + ci][cout]
+  float b[64];
+  float p[64];         // PReLU slopes (SRVGG) when has_prelu
+  int has_prelu;
+};
+
+__global__ void __launch_bounds__(128) first_conv3_const_kernel(const FirstArgs a, const __grid_constant__ FirstWeights3 cw) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int n = blockIdx.z;
+  if (x >= a.W) return;
+  const size_t img = static_cast<size_t>(n) * a.Hs * a.Ws * 3;
+  float in[27];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yy = y + ky - 1, xx = x + kx - 1;
+      const bool ok = yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;   // conv zero padding outside the region
+      const int sy = reflect_src(a.oy + (ok ? yy : 0), a.Hs, a.H1);
+      const int sx = reflect_src(a.ox + (ok ? xx : 0), a.Ws, a.W1);
+      const size_t p = img + (static_cast<size_t>(sy) * a.Ws + sx) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {   // BGR -> RGB, img / max_range as upstream's pre_process
+        const float v = a.src16 ? static_cast<float>(__ldg(reinterpret_cast<const uint16_t*>(a.src) + p + 2 - c)) / 65535.0f
+                                : static_cast<float>(__ldg(a.src + p + 2 - c)) / 255.0f;
+        in[(ky * 3 + kx) * 3 + c] = ok ? v : 0.f;
+      }
+    }
+  const size_t pix = (static_cast<size_t>(n) * a.H + y) * a.W + x;
+  const size_t loff = a.lo ? lo_off(n, y, x, a.H, a.W) : 0;
+  float* f0 = a.f0 ? a.f0 + trunk_off(n, y, x, a.H, a.W) : nullptr;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = cw.b[half * 32 + c];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      const float v = in[t];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] = fmaf(v, cw.w[t][half * 32 + c], acc[c]);
+    }
+    if (cw.has_prelu) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] = acc[c] > 0.f ? acc[c] : acc[c] * cw.p[half * 32 + c];
+    }
+    __nv_bfloat16* o = a.out + pix * a.out_pitch + half * 32;
+    if (a.lo) {   // residual-stream pair: bf16 hi + e5m2 lo of the rounding residual (store_trunk_pair's split)
+      uint32_t l[8];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t p[8];
+        float res[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v0 = acc[g * 16 + 2 * i], v1 = acc[g * 16 + 2 * i + 1];
+          p[i] = pack_bf16x2(v0, v1);
+          res[2 * i] = v0 - bf16lo_f32(p[i]);
+          res[2 * i + 1] = v1 - bf16hi_f32(p[i]);
+        }
+        st_global_256(o + g * 16, p);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) l[g * 4 + i] = f32x4_e5m2(res[4 * i], res[4 * i + 1], res[4 * i + 2], res[4 * i + 3]);
+      }
+      st_global_256(a.lo + loff + half * LO_GSTRIDE, l);
+    } else {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t p[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          p[i] = a.out_fp16 ? pack_f16x2(acc[g * 16 + 2 * i], acc[g * 16 + 2 * i + 1])
+                            : pack_bf16x2(acc[g * 16 + 2 * i], acc[g * 16 + 2 * i + 1]);
+        st_global_256(o + g * 16, p);
+      }
+    }
+    if (f0) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = __float_as_uint(acc[g * 8 + i]);
+        st_global_256(f0 + static_cast<size_t>(half * 4 + g) * TRUNK_GSTRIDE, q);
+      }
+    }
+  }
+  if (a.inrgb) *reinterpret_cast<float4*>(a.inrgb + pix * 4) = make_float4(in[12], in[13], in[14], 0.f);   // centre tap
+}
+
 // out[n][Y][X][:] = in[n][Y/2][X/2][:], 64 bf16 channels (F.interpolate(scale_factor=2, mode='nearest')).
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N,
                                                           int H, int W) {
