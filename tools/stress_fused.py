@@ -1,6 +1,15 @@
 #!/usr/bin/env python
-"""Race hunt for the fused-RDB schedule (dev tool): the per-conv path is the reference, the fused path is repeated
-many times on full-size and ragged inputs; any dependency race shows up as a byte mismatch."""
+"""Adversarial test of the fused-RDB cross-CTA protocol (compute-sanitizer is closed on this pool).
+
+  python tools/stress_fused.py [--iters 60] [--seed 7] [--big]
+
+Every iteration draws a random shape (ragged heights / widths around the strip, flag-block and column-tile
+boundaries), a random batch and a random `max_ctas` between 1 and 148 (fewer resident CTAs than work items, down to
+ONE CTA that must run the whole dependency graph by itself in claim order), runs the per-conv schedule as the
+reference and the fused schedule twice, and compares bytes.  Run it with B200SR_LIB=libb200sr_debug.so to execute
+the build with bounds traps on every flag index, item field and TMA coordinate (`-DB200SR_DEBUG`).
+`--big` adds the full-size shapes (4 x 720p, 1080p x2, the 720p tile regions)."""
+import argparse
 import os
 import sys
 
@@ -10,30 +19,62 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import framewright_b200  # noqa: E402,F401
+from framewright_b200 import _native  # noqa: E402
 from framewright_b200.archs import make_synthetic_state_dict  # noqa: E402
 from framewright_b200.engine import B200Engine  # noqa: E402
 
-reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
-rng = np.random.default_rng(7)
-bad = 0
-for model, shapes in (("RealESRGAN_x4plus", [(4, 720, 1280), (1, 720, 1280)]),
-                      ("RealESRGAN_x4plus_anime_6B", [(8, 256, 256), (2, 522, 532), (3, 218, 266), (2, 333, 517), (5, 40, 1000)]),
-                      ("RealESRGAN_x2plus", [(1, 1080, 1920)])):
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=60)
+    ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--big", action="store_true")
+    args = ap.parse_args()
+    _native.build()
+    print("library:", _native.load().b200sr_version().decode(), flush=True)
+    rng = np.random.default_rng(args.seed)
+    bad = 0
+    model = "RealESRGAN_x4plus_anime_6B"      # 18 fused launches per forward: the protocol, not the depth, is under test
     eng = B200Engine(model, make_synthetic_state_dict(model, 0), gpu_id=0)
-    for n, h, w in shapes:
+    edges = [7, 8, 9, 15, 16, 17, 23, 24, 25, 31, 32, 33, 47, 48, 49, 63, 64, 65]
+    wedges = [8, 31, 127, 128, 129, 255, 256, 257, 300, 383, 385]
+    for it in range(args.iters):
+        n = int(rng.integers(1, 5))
+        h = int(rng.choice(edges)) if rng.random() < 0.5 else int(rng.integers(8, 200))
+        w = int(rng.choice(wedges)) if rng.random() < 0.5 else int(rng.integers(8, 700))
+        ctas = int(rng.choice([1, 2, 3, 5, 8, 17, 37, 74, 147, 148])) if rng.random() < 0.7 else 0
         x = torch.from_numpy(rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)).cuda()
+        eng.set_option("max_ctas", 0)
         eng.set_option("fused_rdb", 0)
         ref = eng.upscale_device(x).clone()
         eng.set_option("fused_rdb", 1)
-        mism = 0
-        for _ in range(reps):
-            got = eng.upscale_device(x)
-            if not torch.equal(got, ref):
-                mism += 1
-        bad += mism
-        print(f"{model} {n}x{h}x{w}: {reps} fused runs, {mism} mismatching", flush=True)
+        eng.set_option("max_ctas", ctas)
+        ok = all(torch.equal(eng.upscale_device(x), ref) for _ in range(2))
+        torch.cuda.synchronize()
+        bad += 0 if ok else 1
+        print(f"[{it:3d}] {n}x{h}x{w} max_ctas={ctas or 148}: {'ok' if ok else 'MISMATCH'}", flush=True)
         del x, ref
+    eng.set_option("max_ctas", 0)
     eng.close()
-    torch.cuda.empty_cache()
-print("STRESS", "FAILED" if bad else "ok")
-sys.exit(1 if bad else 0)
+    if args.big:
+        for mdl, shapes in (("RealESRGAN_x4plus", [(4, 720, 1280)]),
+                            ("RealESRGAN_x4plus_anime_6B", [(8, 256, 256), (2, 522, 532), (3, 218, 266), (5, 40, 1000)]),
+                            ("RealESRGAN_x2plus", [(1, 1080, 1920)])):
+            eng = B200Engine(mdl, make_synthetic_state_dict(mdl, 0), gpu_id=0)
+            for n, h, w in shapes:
+                x = torch.from_numpy(rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)).cuda()
+                eng.set_option("fused_rdb", 0)
+                ref = eng.upscale_device(x).clone()
+                eng.set_option("fused_rdb", 1)
+                mism = sum(0 if torch.equal(eng.upscale_device(x), ref) else 1 for _ in range(5))
+                bad += mism
+                print(f"{mdl} {n}x{h}x{w}: 5 fused runs, {mism} mismatching", flush=True)
+                del x, ref
+            eng.close()
+            torch.cuda.empty_cache()
+    print("STRESS", "FAILED" if bad else "ok", flush=True)
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

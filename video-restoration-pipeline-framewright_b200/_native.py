@@ -14,7 +14,9 @@ from typing import Optional
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
-LIB_PATH = os.path.join(_PKG_DIR, "libb200sr.so")
+# $B200SR_LIB selects another build of the library in the package directory (e.g. libb200sr_debug.so: compiled with
+# -DB200SR_DEBUG, bounds traps in the fused kernel; `build_variant`)
+LIB_PATH = os.path.join(_PKG_DIR, os.environ.get("B200SR_LIB", "libb200sr.so"))
 
 NVCC_FLAGS = [
     "-shared", "-Xcompiler", "-fPIC",
@@ -62,8 +64,29 @@ def needs_build() -> bool:
     return any(os.path.exists(s) and os.path.getmtime(s) > t for s in _sources())
 
 
+def build_variant(name: str, flags, force: bool = False) -> str:
+    """Another build of the library next to the default one, e.g. build_variant("libb200sr_debug.so", ["-DB200SR_DEBUG"])."""
+    path = os.path.join(_PKG_DIR, name)
+    if not force and os.path.exists(path) and all(
+            not os.path.exists(s) or os.path.getmtime(s) <= os.path.getmtime(path) for s in _sources()):
+        return path
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    tmp = path + ".tmp.%d" % os.getpid()
+    proc = subprocess.run([nvcc] + NVCC_FLAGS + list(flags) + ["-o", tmp, os.path.join(CSRC_DIR, "b200sr.cu")],
+                          capture_output=True, text=True)
+    if proc.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+        raise NativeLibraryError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    os.replace(tmp, path)
+    return path
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/b200sr.cu for sm_100a into libb200sr.so next to this file (nvcc cross-compiles without a GPU)."""
+    if os.path.basename(LIB_PATH) != "libb200sr.so":      # a variant selected through $B200SR_LIB
+        flags = ["-DB200SR_DEBUG"] if "debug" in os.path.basename(LIB_PATH) else []
+        return build_variant(os.path.basename(LIB_PATH), flags, force)
     if not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"

@@ -539,6 +539,7 @@ int launch_rdb_fused(b200sr_engine* e, Lane* lane, int li, bool rrdb_end, __nv_b
   a.nitems = lane->rdb_nitems;
   a.flags = lane->d_rdb_flags;
   a.counter = lane->d_rdb_flags + lane->rdb_nflags;
+  a.nflags = lane->rdb_nflags;
   a.flag_target = ((W + 127) / 128) * RDB_NEPI_WARPS;
   a.rrdb_end = rrdb_end ? 1 : 0;
   ++lane->rdb_launch_idx;
@@ -896,7 +897,13 @@ int run_region(b200sr_engine* e, Lane* lane, const Region& R, cudaStream_t st) {
 // =============================================================================== C ABI
 extern "C" {
 
-const char* b200sr_version(void) { return "b200sr 0.1 (sm_100a, tcgen05/TMEM/TMA)"; }
+const char* b200sr_version(void) {
+#ifdef B200SR_DEBUG
+  return "b200sr 0.2 (sm_100a, tcgen05/TMEM/TMA) DEBUG: bounds traps on";
+#else
+  return "b200sr 0.2 (sm_100a, tcgen05/TMEM/TMA)";
+#endif
+}
 
 // Message of the last failed call made by THIS thread (engines are shared between threads); falls back to the
 // engine's most recent message.

@@ -30,6 +30,24 @@
 #define B200SR_ABL_NODEP 0
 #endif
 
+// -DB200SR_DEBUG: bounds traps on everything the cross-CTA protocol indexes with (compute-sanitizer is closed on this
+// pool, so the checks live in the kernel): claimed item fields, completion-counter indices, TMA coordinates.  A
+// violation prints the site and traps (the launch fails with an error instead of corrupting memory silently).
+#ifdef B200SR_DEBUG
+#define RDB_ASSERT(cond, what, a, b)                                                                        \
+  do {                                                                                                      \
+    if (!(cond)) {                                                                                          \
+      printf("B200SR_DEBUG trap: %s (%d, %d) block %d thread %d\n", what, static_cast<int>(a),              \
+             static_cast<int>(b), static_cast<int>(blockIdx.x), static_cast<int>(threadIdx.x));             \
+      __trap();                                                                                             \
+    }                                                                                                       \
+  } while (0)
+#else
+#define RDB_ASSERT(cond, what, a, b) \
+  do {                               \
+  } while (0)
+#endif
+
 namespace b200sr {
 
 struct RdbItem {      // 32 bytes, built on the host (b200sr.cu::build_rdb_items)
@@ -49,6 +67,7 @@ struct RdbArgs {
   int nitems;
   int* flags;             // [frame][conv1..4][block], zeroed before the launch
   int* counter;           // next unclaimed item (zeroed before the launch): items are claimed in list order
+  int nflags;             // number of completion counters (bounds of every flag index; checked in debug builds)
   int flag_target;        // counter value of a complete block: column tiles x epilogue warps
   int rrdb_end;           // conv5 epilogue also applies the RRDB-level skip
   long long* stats;       // optional [grid][16] cycle counters (dev tool; nullptr = off)
@@ -225,6 +244,13 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
         qphase ^= 1;
       }
       if (it < 0) break;
+      RDB_ASSERT(item.k >= 0 && item.k < 5, "item.k", item.k, it);
+      RDB_ASSERT(item.rows >= 1 && item.rows <= (item.k < 4 ? 16 : 8), "item.rows", item.rows, item.k);
+      RDB_ASSERT(item.y0 >= 0 && item.y0 + item.rows <= args.L[item.k].H, "item.y0 + rows", item.y0, item.rows);
+      RDB_ASSERT(item.n >= 0 && item.n < args.L[item.k].N, "item.n", item.n, args.L[item.k].N);
+      RDB_ASSERT(item.tx >= 0 && item.tx * 128 < args.L[item.k].W, "item.tx", item.tx, args.L[item.k].W);
+      RDB_ASSERT(item.k == 4 ? item.flag_base == -1 : (item.flag_base >= 0 && item.flag_base < args.nflags),
+                 "item.flag_base", item.flag_base, args.nflags);
       RDB_STAMP(it, 0);
 #ifdef B200SR_RDB_STATS
       if (args.trace != nullptr && lane == 0) args.trace[static_cast<size_t>(it) * 10 + 8] = blockIdx.x;
@@ -262,6 +288,8 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
           const int bl = (item.y0 > 0 ? item.y0 - 1 : 0) >> RDB_FLAG_SHIFT;
           const int r_hi = item.y0 + item.rows < L.H ? item.y0 + item.rows : L.H - 1;
           const int nb = (r_hi >> RDB_FLAG_SHIFT) - bl + 1;
+          RDB_ASSERT(nb >= 1 && nb <= RDB_MAX_DEP_BLOCKS, "dependency block count", nb, item.rows);
+          RDB_ASSERT(dep + bl >= 0 && dep + bl + nb <= args.nflags, "dependency flag range", dep + bl, nb);
           int m = 0;   // leading complete blocks
           RDB_TIMED(4, {
             if (lane == 0) {
@@ -294,6 +322,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             RDB_TIMED(4, {
               if (lane == 0) {
                 const int* f = args.flags + dep + (r >> RDB_FLAG_SHIFT);
+                RDB_ASSERT(dep >= 0 && dep + (r >> RDB_FLAG_SHIFT) < args.nflags, "lazy dependency flag", dep, r);
                 while (ld_relaxed_gpu(f) < args.flag_target) __nanosleep(B200SR_RDB_POLL_NS);
                 fence_acq_rel_gpu();
                 fence_proxy_async_global();
@@ -304,6 +333,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
           }
           RDB_TIMED(1, mbar_wait(&bar_empty[stage], phase ^ 1));
           if (lane == 0) {   // (the lane that executed the fences above)
+            RDB_ASSERT(r >= -1 && r <= L.H && x0 >= -1 && x0 < L.W && c * L.N + item.n < 3 * L.N, "TMA coordinate", r, x0);
             mbar_arrive_expect_tx(&bar_full[stage], 130 * 128);
             tma_load_4d_hint(&amap, &bar_full[stage], sA + stage * RDB_A_STAGE_BYTES, 0, x0, r, c * L.N + item.n, pol);
           }
@@ -643,6 +673,8 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
           if ((Y & (RDB_FLAG_ROWS - 1)) == RDB_FLAG_ROWS - 1 || Y == item.rows - 1) {
             RDB_TIMED(7, {
               __syncwarp();   // orders every lane's stores before lane 0's release (cumulative at gpu scope)
+              RDB_ASSERT(item.flag_base + ((item.y0 + Y) >> RDB_FLAG_SHIFT) < args.nflags, "release flag index",
+                         item.flag_base, item.y0 + Y);
               if (lane == 0) red_release_gpu_add(args.flags + item.flag_base + ((item.y0 + Y) >> RDB_FLAG_SHIFT), 1);
             });
           }
