@@ -154,7 +154,7 @@ def test_fused_rdb_work_list(native_lib, n, h, w):
     last_writer = np.full((n, 4, nblk), -1, np.int64)     # index of the last item that stores into the block
     for i, (k, fn, y0, rows, tx, fb, d0, d1) in enumerate(items):
         assert 0 <= k < 5 and 1 <= rows <= (16 if k < 4 else 8) and y0 >= 0 and y0 + rows <= h
-        assert y0 % 8 == 0
+        assert y0 % fr == 0       # (the 2-CTAs-per-SM build: 8- / 4-row items on 4-row counter blocks)
         cover[k, fn, y0:y0 + rows, tx] += 1
         if k < 4:
             assert fb == (fn * 4 + k) * nblk

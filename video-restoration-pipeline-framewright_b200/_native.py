@@ -64,6 +64,19 @@ def needs_build() -> bool:
     return any(os.path.exists(s) and os.path.getmtime(s) > t for s in _sources())
 
 
+def variant_flags(name: str):
+    """Compile flags encoded in a variant's file name: *debug* -> bounds traps, *rdb2* -> fused RDB with 2 CTAs per SM,
+    *rdb1* -> 1 CTA per SM."""
+    flags = []
+    if "debug" in name:
+        flags.append("-DB200SR_DEBUG")
+    if "rdb2" in name:
+        flags.append("-DB200SR_RDB_CTAS=2")
+    if "rdb1" in name:
+        flags.append("-DB200SR_RDB_CTAS=1")
+    return flags
+
+
 def build_variant(name: str, flags, force: bool = False) -> str:
     """Another build of the library next to the default one, e.g. build_variant("libb200sr_debug.so", ["-DB200SR_DEBUG"])."""
     path = os.path.join(_PKG_DIR, name)
@@ -85,8 +98,7 @@ def build_variant(name: str, flags, force: bool = False) -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/b200sr.cu for sm_100a into libb200sr.so next to this file (nvcc cross-compiles without a GPU)."""
     if os.path.basename(LIB_PATH) != "libb200sr.so":      # a variant selected through $B200SR_LIB
-        flags = ["-DB200SR_DEBUG"] if "debug" in os.path.basename(LIB_PATH) else []
-        return build_variant(os.path.basename(LIB_PATH), flags, force)
+        return build_variant(os.path.basename(LIB_PATH), variant_flags(os.path.basename(LIB_PATH)), force)
     if not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"

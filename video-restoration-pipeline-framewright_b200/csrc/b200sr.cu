@@ -411,7 +411,7 @@ int ensure_ws(b200sr_engine* e, Lane* lane, size_t bytes, cudaStream_t st) {
 }
 
 // ---- fused RDB: item table (skewed row strips) ------------------------------------------------------
-constexpr int RDB_STRIP = 16;   // rows per strip (= rows per conv1..4 item; conv5 items have 8)
+constexpr int RDB_STRIP = RDB_STRIP_ROWS;   // rows per strip (= rows per conv1..4 item; conv5 items have half)
 int RDB_ORDER[5] = {0, 1, 2, 3, 4};      // order of the convs inside one step of the work list (option rdb_order)
 int RDB_STEP_OFF[5] = {0, 1, 2, 3, 5};
 int RDB_INTERLEAVE = -1;                 // option rdb_interleave (build_rdb_items)   // step in which conv k reaches strip s: s + RDB_STEP_OFF[k] (option rdb_off)
@@ -419,7 +419,7 @@ int RDB_INTERLEAVE = -1;                 // option rdb_interleave (build_rdb_ite
 // Strip s of conv k covers rows [16 s - 8 k, 16 s + 16 - 8 k): every conv is shifted up by 8 rows relative to
 // its predecessor, so the rows an item reads (its own +-1) of a lower conv belong to items earlier in the list.
 void build_rdb_items(int N, int H, int W, std::vector<RdbItem>& items, int* nflags) {
-  const int S = (H + 32 + RDB_STRIP - 1) / RDB_STRIP;
+  const int S = (H + 4 * RDB_SHIFT_ROWS + RDB_STRIP - 1) / RDB_STRIP;
   const int xt = (W + 127) / 128;
   const int nblk = (H + RDB_FLAG_ROWS - 1) / RDB_FLAG_ROWS;   // completion counters per conv and frame
   *nflags = N * 4 * nblk;
@@ -442,9 +442,9 @@ void build_rdb_items(int N, int H, int W, std::vector<RdbItem>& items, int* nfla
         // conv5 items are short and reach their dependent chunk early.
         const int s = t - RDB_STEP_OFF[k];
         if (s < 0 || s >= S) continue;
-        const int lo = std::max(0, s * RDB_STRIP - 8 * k), hi = std::min(H, (s + 1) * RDB_STRIP - 8 * k);
+        const int lo = std::max(0, s * RDB_STRIP - RDB_SHIFT_ROWS * k), hi = std::min(H, (s + 1) * RDB_STRIP - RDB_SHIFT_ROWS * k);
         if (lo >= hi) continue;
-        const int th = k < 4 ? 16 : 8;
+        const int th = k < 4 ? RDB_TH4 : RDB_TH5;
         for (int y0 = lo; y0 < hi; y0 += th)
           for (int tx = 0; tx < xt; ++tx) {
             RdbItem it{};
@@ -544,11 +544,11 @@ int launch_rdb_fused(b200sr_engine* e, Lane* lane, int li, bool rrdb_end, __nv_b
   a.rrdb_end = rrdb_end ? 1 : 0;
   ++lane->rdb_launch_idx;
   if (lane->rdb_launch_idx == -e->opt_rdb_stats) {   // negative: cycle counters only (no per-item / per-row stamps)
-    if (!e->d_rdb_stats) CUDA_TRY(e, cudaMalloc(&e->d_rdb_stats, 148 * 16 * sizeof(long long)));
+    if (!e->d_rdb_stats) CUDA_TRY(e, cudaMalloc(&e->d_rdb_stats, 296 * 16 * sizeof(long long)));
     a.stats = e->d_rdb_stats;
   }
   if (e->opt_rdb_stats > 0 && lane->rdb_launch_idx == e->opt_rdb_stats) {   // dev tool, single-threaded use only
-    if (!e->d_rdb_stats) CUDA_TRY(e, cudaMalloc(&e->d_rdb_stats, 148 * 16 * sizeof(long long)));
+    if (!e->d_rdb_stats) CUDA_TRY(e, cudaMalloc(&e->d_rdb_stats, 296 * 16 * sizeof(long long)));
     a.stats = e->d_rdb_stats;
     if (e->stats_nitems != lane->rdb_nitems) {
       if (e->d_rdb_trace) cudaFree(e->d_rdb_trace);
@@ -570,7 +570,7 @@ int launch_rdb_fused(b200sr_engine* e, Lane* lane, int li, bool rrdb_end, __nv_b
   }
   ProfScope prof_scope(e, PC_RDB_FUSED, flops, st);
   CUDA_TRY(e, cudaMemsetAsync(lane->d_rdb_flags, 0, static_cast<size_t>(lane->rdb_nflags + 1) * sizeof(int), st));
-  const int grid = std::min(a.nitems, e->opt_max_ctas > 0 ? e->opt_max_ctas : e->num_sms);
+  const int grid = std::min(a.nitems, e->opt_max_ctas > 0 ? e->opt_max_ctas : e->num_sms * RDB_CTAS);
   rdb_fused_kernel<<<grid, RDB_NTHREADS, RDB_SMEM_BYTES, st>>>(amap, a);
   CUDA_TRY(e, cudaGetLastError());
   lane->launches++;
@@ -901,7 +901,8 @@ const char* b200sr_version(void) {
 #ifdef B200SR_DEBUG
   return "b200sr 0.2 (sm_100a, tcgen05/TMEM/TMA) DEBUG: bounds traps on";
 #else
-  return "b200sr 0.2 (sm_100a, tcgen05/TMEM/TMA)";
+  return RDB_CTAS == 2 ? "b200sr 0.2 (sm_100a, tcgen05/TMEM/TMA) fused RDB: 2 CTAs per SM"
+                       : "b200sr 0.2 (sm_100a, tcgen05/TMEM/TMA)";
 #endif
 }
 

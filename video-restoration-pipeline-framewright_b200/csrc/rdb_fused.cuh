@@ -147,28 +147,46 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 #define B200SR_RDB_POLL_NS 64
 #endif
 constexpr int RDB_QD = B200SR_RDB_QD;
+// CTAs per SM.  1 (default): one persistent CTA per SM with all 512 TMEM columns -- items of 16 rows (conv5: 8), two
+// weight-chunk buffers, four activation stages, eight epilogue warps.  2: two co-resident CTAs with 256 TMEM columns
+// each -- items of 8 rows (conv5: 4), ONE weight buffer, two activation stages, four epilogue warps -- so that the
+// issue bubbles of one CTA (barrier waits between bursts, weight reloads, dependency waits) are filled by the other
+// CTA's MMAs on the shared tensor pipe, and the L2 working set of the skewed schedule halves.
+#ifndef B200SR_RDB_CTAS
+#define B200SR_RDB_CTAS 1
+#endif
+constexpr int RDB_CTAS = B200SR_RDB_CTAS;
+static_assert(RDB_CTAS == 1 || RDB_CTAS == 2, "B200SR_RDB_CTAS must be 1 or 2");
+constexpr int RDB_TMEM_COLS = 512 / RDB_CTAS;
+constexpr int RDB_TH4 = RDB_TMEM_COLS / 32;        // output rows of a conv1..4 item (one 32-column slot per row)
+constexpr int RDB_TH5 = RDB_TMEM_COLS / 64;        // output rows of a conv5 item
+constexpr int RDB_STRIP_ROWS = RDB_TH4;            // rows per strip of the skewed schedule
+constexpr int RDB_SHIFT_ROWS = RDB_TH4 / 2;        // conv k is shifted up by k * RDB_SHIFT_ROWS rows
 #ifndef B200SR_RDB_FLAG_SHIFT
-#define B200SR_RDB_FLAG_SHIFT 3
+#define B200SR_RDB_FLAG_SHIFT (B200SR_RDB_CTAS == 1 ? 3 : 2)
 #endif
 constexpr int RDB_FLAG_SHIFT = B200SR_RDB_FLAG_SHIFT;   // completion counters per 2^shift output rows of a conv
 constexpr int RDB_FLAG_ROWS = 1 << RDB_FLAG_SHIFT;
-constexpr int RDB_MAX_DEP_BLOCKS = 18 / RDB_FLAG_ROWS + 2;
-constexpr int RDB_NSTAGES = 4;
+static_assert(RDB_FLAG_ROWS <= RDB_SHIFT_ROWS, "item rows must start on a completion-counter block boundary");
+constexpr int RDB_MAX_DEP_BLOCKS = (RDB_TH4 + 2) / RDB_FLAG_ROWS + 2;
+constexpr int RDB_NSTAGES = RDB_CTAS == 1 ? 4 : 2;
+constexpr int RDB_NWBUF = RDB_CTAS == 1 ? 2 : 1;
 constexpr int RDB_WBUF_BYTES = 9 * 64 * 128;                 // weight chunk buffer sized for Cout = 64
 constexpr int RDB_A_STAGE_BYTES = 17 * 1024;
-constexpr int RDB_SMEM_BYTES = 2 * RDB_WBUF_BYTES + RDB_NSTAGES * RDB_A_STAGE_BYTES + 1024;
-constexpr int RDB_NEPI_WARPS = 8;
+constexpr int RDB_SMEM_BYTES = RDB_NWBUF * RDB_WBUF_BYTES + RDB_NSTAGES * RDB_A_STAGE_BYTES + 1024;
+constexpr int RDB_NEPI_WARPS = RDB_CTAS == 1 ? 8 : 4;
+constexpr int RDB_NGRP = RDB_NEPI_WARPS / 4;                 // epilogue groups (one warp per TMEM lane quarter each)
 constexpr int RDB_NTHREADS = 32 * (2 + RDB_NEPI_WARPS);
 
-__global__ void __launch_bounds__(RDB_NTHREADS, 1)
+__global__ void __launch_bounds__(RDB_NTHREADS, RDB_CTAS)
 rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ RdbArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;
-  uint8_t* sA = smem + 2 * RDB_WBUF_BYTES;
+  uint8_t* sA = smem + RDB_NWBUF * RDB_WBUF_BYTES;
 
   __shared__ uint64_t bar_full[RDB_NSTAGES], bar_empty[RDB_NSTAGES];
-  __shared__ uint64_t bar_wfull[2], bar_wempty[2];
+  __shared__ uint64_t bar_wfull[RDB_NWBUF], bar_wempty[RDB_NWBUF];
   __shared__ uint64_t bar_rfull[16], bar_rempty[16];   // one per 32-column TMEM slot
   __shared__ uint64_t bar_qfull[RDB_QD], bar_qempty[RDB_QD];   // claimed-item queue: producer -> MMA + epilogue warps
   __shared__ int s_q[RDB_QD];
@@ -188,7 +206,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < RDB_NWBUF; ++i) {
       mbar_init(&bar_wfull[i], 1);
       mbar_init(&bar_wempty[i], 1);
     }
@@ -204,7 +222,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
     tma_prefetch_desc(&amap);
   }
   if (warp == 1) {
-    tmem_alloc(&s_tmem_base, 512);
+    tmem_alloc(&s_tmem_base, RDB_TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -245,7 +263,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
       }
       if (it < 0) break;
       RDB_ASSERT(item.k >= 0 && item.k < 5, "item.k", item.k, it);
-      RDB_ASSERT(item.rows >= 1 && item.rows <= (item.k < 4 ? 16 : 8), "item.rows", item.rows, item.k);
+      RDB_ASSERT(item.rows >= 1 && item.rows <= (item.k < 4 ? RDB_TH4 : RDB_TH5), "item.rows", item.rows, item.k);
       RDB_ASSERT(item.y0 >= 0 && item.y0 + item.rows <= args.L[item.k].H, "item.y0 + rows", item.y0, item.rows);
       RDB_ASSERT(item.n >= 0 && item.n < args.L[item.k].N, "item.n", item.n, args.L[item.k].N);
       RDB_ASSERT(item.tx >= 0 && item.tx * 128 < args.L[item.k].W, "item.tx", item.tx, args.L[item.k].W);
@@ -343,8 +361,10 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             phase ^= 1;
           }
         }
-        wb ^= 1;
-        if (wb == 0) wphase ^= 1;
+        if (++wb == RDB_NWBUF) {
+          wb = 0;
+          wphase ^= 1;
+        }
       }
       RDB_STAMP(it, 5);
     }
@@ -559,8 +579,10 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
           }
         }
         for (; y <= TH; y += 2) burst(y, (y + 1 <= TH) ? 2 : 1);
-        wb ^= 1;
-        if (wb == 0) wphase ^= 1;
+        if (++wb == RDB_NWBUF) {
+          wb = 0;
+          wphase ^= 1;
+        }
       }
       RDB_STAMP(it, 6);
     }
@@ -599,7 +621,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
         // pull the residual (lo) rows of this item towards L2 while the MMAs run (2 groups x 1 KB per warp-row); the
         // x.hi rows arrive with the chunk-0 TMA loads.  At the RRDB end also x0.lo of the RRDB input pair (last
         // touched three launches ago; prefetching x0.hi as well measured ~1 % slower, more early DRAM traffic).
-        for (int Y = eg; Y < item.rows; Y += 2) {
+        for (int Y = eg; Y < item.rows; Y += RDB_NGRP) {
           const size_t o = lo_off(n, item.y0 + Y, item.tx * 128 + q * 32, L.H, L.W) + (lane & 7) * 128 +
                            static_cast<size_t>((lane >> 3) & 1) * LO_GSTRIDE;
           if (lane < 16) {
@@ -609,7 +631,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
         }
         for (int Y = 0; Y < item.rows; ++Y) {
           const int sl = 2 * Y;
-          if ((Y & 1) == eg) {
+          if ((Y % RDB_NGRP) == eg) {
             // Request one of this pixel's pairs now, while the MMAs of the row are still in flight: the RDB input
             // pair x, or at the RRDB end the RRDB input pair x0 -- x0 was last touched three launches ago and
             // comes from DRAM, x is L2-warm (chunk-0 TMA loads, lo prefetch) and is fetched after the accumulators.
@@ -651,7 +673,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
         }
       } else {
         for (int Y = 0; Y < item.rows; ++Y) {
-          if ((Y & 1) == eg) {
+          if ((Y % RDB_NGRP) == eg) {
             RDB_TIMED(0, mbar_wait(&bar_rfull[Y], (rfull_par >> Y) & 1u));
             if (q == 2 && lane == 0) RDB_STAMP2(it, Y, 1);
             tc_fence_after();
@@ -696,7 +718,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, RDB_TMEM_COLS);
 }
 
 }  // namespace b200sr
