@@ -273,3 +273,22 @@ def test_engine_load_is_strict(native_lib):
     with pytest.raises(EngineError, match="shape"):
         B200Engine(name, bad, gpu_id=0)
     B200Engine(name, sd, gpu_id=0).close()
+
+
+def test_engine_workspace_formula_matches_the_c_abi(native_lib):
+    """`tile_sizing.engine_workspace_bytes` (pure Python, used for tile-size decisions without touching the device)
+    equals `b200sr_workspace_bytes` for every architecture, whole frames, tiles, pads and batches."""
+    from framewright_b200.archs import make_synthetic_state_dict
+    from framewright_b200.engine import B200Engine
+    from framewright_b200.tile_sizing import calculate_optimal_tile_size, engine_workspace_bytes
+
+    for name in ("RealESRGAN_x4plus_anime_6B", "RealESRGAN_x2plus", "realesr-animevideov3"):
+        eng = B200Engine(name, make_synthetic_state_dict(name, 0), gpu_id=0)
+        for (n, h, w, tile, pad, pre) in [(1, 720, 1280, 0, 10, 0), (4, 720, 1280, 0, 10, 0), (2, 721, 1279, 512, 10, 10),
+                                          (8, 256, 256, 0, 10, 0), (1, 1080, 1920, 400, 10, 0), (3, 45, 63, 32, 4, 3)]:
+            assert eng.workspace_bytes(n, h, w, tile, pad, pre) == engine_workspace_bytes(name, w, h, n, tile, pad, pre), \
+                (name, n, h, w, tile, pad, pre)
+        eng.close()
+    free_mb = torch.cuda.mem_get_info(0)[0] >> 20
+    assert calculate_optimal_tile_size((1280, 720), 4, available_vram_mb=free_mb) == 0      # a 720p frame fits whole
+    assert calculate_optimal_tile_size((1280, 720), 4, available_vram_mb=2000) >= 128

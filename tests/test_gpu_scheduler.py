@@ -78,3 +78,49 @@ def test_frame_arrays_and_ordered_stream_through_the_pool(setup):
     res = pool.stream(iter(frames), d._esr_config(), emit, num_frames=n, frame_shape=(h, w), scale=4, batch=2, window=8)
     assert not res.errors and order == list(range(n))
     assert all(np.array_equal(got[i], want[i]) for i in range(n))
+
+
+def test_batch_path_facade_and_process_frames_on_the_device(setup, tmp_path):
+    """The callers either side of the path with REAL engines: `enhance_frames_batched` (checkpoint + progress per
+    frame), `SuperResolution(...).upscale(dir, dir)` / `.process(list)`, `multi_gpu_process_frames`."""
+    import types
+
+    import cv2
+
+    from framewright_b200.pytorch_realesrgan import PyTorchESRGANConfig
+    from framewright_b200.restorer_adapter import enhance_frames_batched, multi_gpu_process_frames
+    from framewright_b200.super_resolution import SRConfig, SuperResolution
+
+    d, gpus, frames, want = setup
+    ind = tmp_path / "frames"
+    ind.mkdir()
+    paths = []
+    for i, f in enumerate(frames[:9]):
+        p = ind / f"frame_{i + 1:08d}.png"
+        cv2.imwrite(str(p), f)
+        paths.append(p)
+    # f2: the batch path behind VideoRestorer.enhance_frames
+    updates, prog = [], []
+    cm = types.SimpleNamespace(load_checkpoint=lambda: None, update_stage=lambda s: updates.append(("stage", s)),
+                               update_frame=lambda **k: updates.append(("frame", k["frame_number"], str(k["output_path"]))),
+                               get_unprocessed_frames=lambda fs: fs, force_save=lambda: None)
+    cfg = PyTorchESRGANConfig(model_name=NAME, scale_factor=4)
+    n = enhance_frames_batched(paths, tmp_path / "enhanced", cfg, checkpoint_manager=cm, distributor=d,
+                               update_progress=lambda **k: prog.append(k["frames_completed"]))
+    assert n == 9 and updates[0] == ("stage", "enhance") and sorted(u[1] for u in updates[1:]) == list(range(1, 10))
+    assert prog[0] == 0 and sorted(prog[1:-1]) == list(range(1, 10))
+    for i in range(9):
+        assert np.array_equal(cv2.imread(str(tmp_path / "enhanced" / f"frame_{i + 1:08d}.png"), cv2.IMREAD_UNCHANGED), want[i])
+    # a9: the facade, frames directory and frame list
+    sr = SuperResolution(SRConfig(scale=4, backend="realesrgan_anime"))
+    res = sr.upscale(ind, tmp_path / "sr_out")
+    assert res.frames_processed == 9 and res.frames_failed == 0 and res.backend_used == "realesrgan_anime"
+    assert np.array_equal(cv2.imread(str(tmp_path / "sr_out" / "frame_00000004.png"), cv2.IMREAD_UNCHANGED), want[3])
+    outs = sr.process([f for f in frames[:5]], scale=4)
+    assert all(np.array_equal(o, w) for o, w in zip(outs, want[:5]))
+    sr.clear_cache()
+    # f4: MultiGPUProcessor.process_frames shape over shared memory
+    pool = d._get_pool([g.id for g in gpus])
+    results = multi_gpu_process_frames([f for f in frames[:7]], cfg, pool=pool)
+    assert [r.frame_index for r in results] == list(range(7)) and all(r.success for r in results)
+    assert all(np.array_equal(r.output, want[r.frame_index]) for r in results)
