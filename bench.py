@@ -183,7 +183,9 @@ def bench_configs(torch, peaks):
         ("cfg1_x4plus_256x256_batch8", "RealESRGAN_x4plus", 8, 256, 256, {}, 1.0),
         ("cfg2_general_x4v3_640x480_batch64", "realesr-general-x4v3", 64, 480, 640, {}, 1.0),
         ("cfg3_x2plus_1080p", "RealESRGAN_x2plus", 2, 1080, 1920, {}, 0.25),          # MACs are per unshuffled pixel
-        ("cfg4_x4plus_720p_tile512_pad10", "RealESRGAN_x4plus", 2, 720, 1280, {"tile": 512, "tile_pad": 10}, 976800 / 921600),
+        ("cfg4_x4plus_720p_tile512_pad10", "RealESRGAN_x4plus", 4, 720, 1280, {"tile": 512, "tile_pad": 10}, 976800 / 921600),
+        # the CLI's variant (cli.py:742-750: pre_pad = 10): tiles over the 1290x730 padded image, 997 500 px processed
+        ("cfg4_cli_prepad10", "RealESRGAN_x4plus", 4, 720, 1280, {"tile": 512, "tile_pad": 10, "pre_pad": 10}, 997500 / 921600),
     ]
     out = {}
     for key, name, n, h, w, kw, px_factor in cases:

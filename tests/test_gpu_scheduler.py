@@ -124,3 +124,23 @@ def test_batch_path_facade_and_process_frames_on_the_device(setup, tmp_path):
     results = multi_gpu_process_frames([f for f in frames[:7]], cfg, pool=pool)
     assert [r.frame_index for r in results] == list(range(7)) and all(r.success for r in results)
     assert all(np.array_equal(r.output, want[r.frame_index]) for r in results)
+
+
+def test_raw_video_pipe_through_the_gpus(setup):
+    """f1: raw bgr24 frames from a pipe -> ordered shared-memory ring over the GPUs -> raw bgr24 frames to a pipe."""
+    import io
+
+    from framewright_b200.pytorch_realesrgan import PyTorchESRGANConfig
+    from framewright_b200.restorer_adapter import upscale_raw_stream
+
+    d, gpus, frames, want = setup
+    pool = d._get_pool([g.id for g in gpus])
+    n, h, w = frames.shape[:3]
+    src, dst = io.BytesIO(frames.tobytes()), io.BytesIO()
+    cfg = PyTorchESRGANConfig(model_name=NAME, scale_factor=4)
+    assert upscale_raw_stream(src, dst, w, h, cfg, num_frames=n, pool=pool) == n
+    assert np.array_equal(np.frombuffer(dst.getvalue(), np.uint8).reshape(want.shape), want)
+    # single engine in this process (no pool): same bytes
+    src, dst = io.BytesIO(frames[:6].tobytes()), io.BytesIO()
+    assert upscale_raw_stream(src, dst, w, h, cfg, num_frames=6, batch=4) == 6
+    assert np.array_equal(np.frombuffer(dst.getvalue(), np.uint8).reshape(want[:6].shape), want[:6])
