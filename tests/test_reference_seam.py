@@ -11,6 +11,8 @@ import os
 import sys
 import types
 
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -100,3 +102,89 @@ def test_reference_and_mirror_expose_same_surface(ref_modules):
     ref_fields = [(f.name, f.default) for f in dataclasses.fields(pr.PyTorchESRGANConfig)]
     my_fields = [(f.name, f.default) for f in dataclasses.fields(mine.PyTorchESRGANConfig)]
     assert ref_fields == my_fields
+
+
+def _reference_method(path, cls, name):
+    """Source of one method of the reference, verbatim, as a plain function (the module itself cannot be imported:
+    `framewright.restorer` pulls in `framewright.infrastructure.models`, which does not exist in the reference tree)."""
+    import ast
+    import textwrap
+
+    src = open(path).read()
+    tree = ast.parse(src)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef) and node.name == cls:
+            for fn in node.body:
+                if isinstance(fn, ast.FunctionDef) and fn.name == name:
+                    return textwrap.dedent("\n".join(src.splitlines()[fn.lineno - 1:fn.end_lineno]))
+    raise AssertionError(f"{cls}.{name} not found in {path}")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_video_restorer_enhance_stage_runs_verbatim_against_the_mirror(tmp_path, monkeypatch):
+    """`VideoRestorer._enhance_single_frame_pytorch` (restorer.py:1420-1460) -- the reference's caller,
+    its source text unmodified -- executed against this repo's module functions: ncnn model name -> config ->
+    `enhance_frame_pytorch` -> output validation, returning `(output_path, ok, err)`; and the "memory" error string
+    its retry ladder greps for (:1746)."""
+    import types
+    from typing import Optional, Tuple
+
+    import cv2
+    import torch
+
+    from framewright_b200 import pytorch_realesrgan as mine
+    from framewright_b200 import upsampler as up_mod
+    from framewright_b200.archs import make_synthetic_state_dict
+    from framewright_b200.engine import EngineOutOfMemory
+    from framewright_b200.restorer_adapter import validate_frame_integrity
+    from oracle import oracle
+
+    fail = {"oom": False}
+
+    class OracleEngine:
+        def __init__(self, arch, state_dict, gpu_id=0):
+            self.name = next(k for k, v in up_mod.MODEL_ARCHS.items() if v == arch)
+            self.sd = state_dict
+
+        def upscale_host(self, frames, out=None, tile=0, tile_pad=10, pre_pad=0):
+            if fail["oom"]:
+                raise EngineOutOfMemory("GPU out of memory: out of memory allocating 6300 MiB workspace")
+            return oracle.make_upsampler(self.name, self.sd, tile=tile, tile_pad=tile_pad, pre_pad=pre_pad).enhance(frames)[0]
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(up_mod, "B200Engine", OracleEngine)
+    monkeypatch.setattr(mine, "is_pytorch_esrgan_available", lambda: True)
+    monkeypatch.setattr(mine, "_auto_tile", lambda gpu: 0)
+    monkeypatch.setattr(mine, "_available_vram_mb", lambda gpu: 50000.0)
+    wdir = tmp_path / "weights"
+    wdir.mkdir()
+    torch.save({"params_ema": make_synthetic_state_dict("RealESRGAN_x4plus_anime_6B", 0)},
+               str(wdir / "RealESRGAN_x4plus_anime_6B.pth"))
+    monkeypatch.setenv("B200SR_WEIGHTS_DIR", str(wdir))
+    mine.clear_upsampler_cache()
+
+    ns = {"Path": Path, "Tuple": Tuple, "Optional": Optional,
+          "is_pytorch_esrgan_available": mine.is_pytorch_esrgan_available,
+          "convert_ncnn_model_name": mine.convert_ncnn_model_name, "PyTorchESRGANConfig": mine.PyTorchESRGANConfig,
+          "enhance_frame_pytorch": mine.enhance_frame_pytorch, "validate_frame_integrity": validate_frame_integrity}
+    exec(_reference_method(os.path.join(REF, "restorer.py"), "VideoRestorer", "_enhance_single_frame_pytorch"), ns)
+    restorer = types.SimpleNamespace(config=types.SimpleNamespace(model_name="realesrgan-x4plus-anime", scale_factor=4,
+                                                                  gpu_id=None))
+    img = oracle.synthetic_frame(20, 24, seed=5, kind="mixed")
+    src, dst = tmp_path / "frame_00000001.png", tmp_path / "enhanced_frame_00000001.png"
+    cv2.imwrite(str(src), img)
+    out_path, ok, err = ns["_enhance_single_frame_pytorch"](restorer, src, dst, 0)
+    assert (out_path, ok, err) == (dst, True, None)
+    got = cv2.imread(str(dst), cv2.IMREAD_UNCHANGED)
+    want = oracle.make_upsampler("RealESRGAN_x4plus_anime_6B", make_synthetic_state_dict("RealESRGAN_x4plus_anime_6B", 0),
+                                 tile=0, pre_pad=0).enhance(img)[0]
+    assert np.array_equal(got, want)
+    v = validate_frame_integrity(dst)
+    assert v.is_valid and (v.width, v.height) == (96, 80)
+    fail["oom"] = True
+    _, ok, err = ns["_enhance_single_frame_pytorch"](restorer, src, tmp_path / "o2.png", 0)
+    assert ok is False and ("vram" in err.lower() or "memory" in err.lower())         # restorer.py:1746's test
+    assert not validate_frame_integrity(tmp_path / "o2.png").is_valid
+    mine.clear_upsampler_cache()

@@ -149,6 +149,63 @@ def enhance_frames_batched(frames: Sequence[Path], enhanced_dir: Path, config: P
     return state["enhanced"] + (total_all - total)
 
 
+# ------------------------------------------------------------------------------------------------ f1: no ffprobe fork
+@dataclass
+class FrameValidation:
+    """Mirror of `framewright.validators.FrameValidation` (:47-55)."""
+    frame_path: Path
+    is_valid: bool
+    width: int = 0
+    height: int = 0
+    file_size: int = 0
+    error_message: Optional[str] = None
+    quality: Any = None
+
+
+def validate_frame_integrity(frame_path: Path) -> FrameValidation:
+    """`validators.validate_frame_integrity` (:143-200) without forking `ffprobe` for every frame: the same checks
+    (exists, non-empty, a decodable image header with non-zero dimensions) by reading the PNG IHDR / JPEG SOF marker.
+    At 27 frames/s per GPU a process fork per output frame is the pipeline bound the survey measured (f1)."""
+    frame_path = Path(frame_path)
+    result = FrameValidation(frame_path=frame_path, is_valid=False)
+    if not frame_path.exists():
+        result.error_message = "File does not exist"
+        return result
+    result.file_size = frame_path.stat().st_size
+    if result.file_size == 0:
+        result.error_message = "File is empty"
+        return result
+    try:
+        with open(frame_path, "rb") as f:
+            head = f.read(32)
+            if head[:8] == b"\x89PNG\r\n\x1a\n" and head[12:16] == b"IHDR":
+                result.width = int.from_bytes(head[16:20], "big")
+                result.height = int.from_bytes(head[20:24], "big")
+            elif head[:2] == b"\xff\xd8":                      # JPEG: walk the segments to the first SOFn marker
+                f.seek(2)
+                while True:
+                    b = f.read(4)
+                    if len(b) < 4 or b[0] != 0xFF:
+                        break
+                    marker, seglen = b[1], int.from_bytes(b[2:4], "big")
+                    if 0xC0 <= marker <= 0xCF and marker not in (0xC4, 0xC8, 0xCC):
+                        d = f.read(5)
+                        result.height, result.width = int.from_bytes(d[1:3], "big"), int.from_bytes(d[3:5], "big")
+                        break
+                    f.seek(seglen - 2, 1)
+            else:
+                result.error_message = "No video stream found"
+                return result
+    except OSError as e:
+        result.error_message = f"read error: {e}"
+        return result
+    if result.width == 0 or result.height == 0:
+        result.error_message = "Invalid dimensions"
+        return result
+    result.is_valid = True
+    return result
+
+
 # ------------------------------------------------------------------------------------------------ f4
 def make_streaming_enhancer(config: PyTorchESRGANConfig, load: Optional[Callable[[Path], np.ndarray]] = None,
                             upsampler: Any = None) -> Callable[[List[Any]], List[Any]]:

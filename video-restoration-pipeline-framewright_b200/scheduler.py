@@ -107,14 +107,8 @@ class SharedArray:
     def __setstate__(self, st):
         self.shape, self.dtype, self.name_ = st["shape"], st["dtype"], st["name_"]
         self._shm = shared_memory.SharedMemory(name=self.name_)
-        self._owner = False
+        self._owner = False        # (spawned workers share the parent's resource tracker: attaching does not unlink)
         self._pinned = False
-        try:   # the attaching process must not unlink the segment when it exits (bpo-38119)
-            from multiprocessing import resource_tracker
-
-            resource_tracker.unregister(self._shm._name, "shared_memory")
-        except Exception:  # pragma: no cover
-            pass
 
     def pin(self) -> bool:
         if self._pinned:
@@ -141,6 +135,9 @@ class SharedArray:
             self._pinned = False
 
     def release(self) -> None:
+        """Un-pin, unmap, and (creator only) unlink.  Idempotent."""
+        if self._shm is None:
+            return
         try:
             self.unpin()
         except Exception:
@@ -149,6 +146,13 @@ class SharedArray:
             self._shm.close()
             if self._owner:
                 self._shm.unlink()
+        except Exception:
+            pass
+        self._shm = None
+
+    def __del__(self):  # pragma: no cover - safety net: never leave a registration behind an unmapped segment
+        try:
+            self.release()
         except Exception:
             pass
 
@@ -170,6 +174,12 @@ class ArraySource(FrameSource):
 
     def open(self) -> None:
         self.shared.pin()
+
+    def close(self) -> None:
+        # in the worker: un-pin BEFORE the mapping goes away -- a page-locked registration that outlives its mapping
+        # would make a later segment mapped at the same address look pinned and DMA into freed pages
+        if not self.shared._owner:
+            self.shared.release()
 
     def slot(self, i: int) -> int:
         return i % self.shared.shape[0]
@@ -222,6 +232,10 @@ class ArraySink(FrameSink):
 
     def open(self) -> None:
         self.shared.pin()
+
+    def close(self) -> None:
+        if not self.shared._owner:      # worker side: un-pin, then unmap (see ArraySource.close)
+            self.shared.release()
 
     def out_block(self, i0: int, k: int, shape: Tuple[int, ...]) -> Optional[np.ndarray]:
         a = self.shared.array
