@@ -302,14 +302,23 @@ __global__ void __launch_bounds__(128) first_conv3_const_kernel(const FirstArgs 
   float* f0 = a.f0 ? a.f0 + trunk_off(n, y, x, a.H, a.W) : nullptr;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
-    float acc[32];
+    // packed fp32 FMAs (FFMA2: two IEEE fma.rn per instruction -- same bits as scalar fmaf): the accumulators of two
+    // adjacent channels form a pair, the input value is broadcast, the weight pair comes from a uniform register
+    float2 acc2[16];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) acc[c] = cw.b[half * 32 + c];
+    for (int c = 0; c < 16; ++c) acc2[c] = make_float2(cw.b[half * 32 + 2 * c], cw.b[half * 32 + 2 * c + 1]);
 #pragma unroll
     for (int t = 0; t < 27; ++t) {
-      const float v = in[t];
+      const float2 vv = make_float2(in[t], in[t]);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) acc[c] = fmaf(v, cw.w[t][half * 32 + c], acc[c]);
+      for (int c = 0; c < 16; ++c)
+        acc2[c] = __ffma2_rn(vv, make_float2(cw.w[t][half * 32 + 2 * c], cw.w[t][half * 32 + 2 * c + 1]), acc2[c]);
+    }
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      acc[2 * c] = acc2[c].x;
+      acc[2 * c + 1] = acc2[c].y;
     }
     if (cw.has_prelu) {
 #pragma unroll
