@@ -274,7 +274,7 @@ struct FirstWeights3 {
   int has_prelu;
 };
 
-__global__ void __launch_bounds__(128) first_conv3_const_kernel(const FirstArgs a, const __grid_constant__ FirstWeights3 cw) {
+__global__ void __launch_bounds__(128, 5) first_conv3_const_kernel(const FirstArgs a, const __grid_constant__ FirstWeights3 cw) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int n = blockIdx.z;
