@@ -74,8 +74,14 @@ struct Lane {
   cudaStream_t stream = nullptr;
   uint8_t* ws = nullptr;          // workspace (grow-only)
   size_t ws_bytes = 0;
-  // fused-RDB item table (depends only on N, H, W) and its counters
-  int rdb_n = 0, rdb_h = 0, rdb_w = 0, rdb_nitems = 0, rdb_nflags = 0, rdb_gen = -1;
+  // fused-RDB item tables (one per (N, H, W): tile mode walks six region shapes per frame) and their counters
+  struct RdbTable {
+    int n = 0, h = 0, w = 0, gen = -1, nitems = 0, nflags = 0;
+    RdbItem* d_items = nullptr;
+    int* d_flags = nullptr;
+  };
+  std::vector<RdbTable> rdb_tables;
+  int rdb_nitems = 0, rdb_nflags = 0;      // of the table selected by the last ensure_rdb_table
   RdbItem* d_rdb_items = nullptr;
   int* d_rdb_flags = nullptr;
   int rdb_launch_idx = 0;
@@ -466,27 +472,49 @@ void build_rdb_items(int N, int H, int W, std::vector<RdbItem>& items, int* nfla
 }
 
 int ensure_rdb_table(b200sr_engine* e, Lane* lane, int N, int H, int W, cudaStream_t st) {
-  if (lane->d_rdb_items && lane->rdb_n == N && lane->rdb_h == H && lane->rdb_w == W && lane->rdb_gen == e->rdb_gen)
-    return B200SR_OK;
-  CUDA_TRY(e, cudaStreamSynchronize(st));
-  if (lane->d_rdb_items) cudaFree(lane->d_rdb_items);
-  if (lane->d_rdb_flags) cudaFree(lane->d_rdb_flags);
-  lane->d_rdb_items = nullptr;
-  lane->d_rdb_flags = nullptr;
+  for (auto& t : lane->rdb_tables)
+    if (t.n == N && t.h == H && t.w == W && t.gen == e->rdb_gen) {
+      lane->d_rdb_items = t.d_items;
+      lane->d_rdb_flags = t.d_flags;
+      lane->rdb_nitems = t.nitems;
+      lane->rdb_nflags = t.nflags;
+      return B200SR_OK;
+    }
+  if (lane->rdb_tables.size() >= 24) {   // shapes come and go (variable frame sizes): drop the oldest table
+    CUDA_TRY(e, cudaStreamSynchronize(st));
+    cudaFree(lane->rdb_tables.front().d_items);
+    cudaFree(lane->rdb_tables.front().d_flags);
+    lane->rdb_tables.erase(lane->rdb_tables.begin());
+  }
   std::vector<RdbItem> items;
   int nflags = 0;
   build_rdb_items(N, H, W, items, &nflags);
-  CUDA_TRY(e, cudaMalloc(&lane->d_rdb_items, items.size() * sizeof(RdbItem)));
-  CUDA_TRY(e, cudaMalloc(&lane->d_rdb_flags, static_cast<size_t>(nflags + 1) * sizeof(int)));   // + item counter
+  Lane::RdbTable t;
+  CUDA_TRY(e, cudaMalloc(&t.d_items, items.size() * sizeof(RdbItem)));
+  cudaError_t err = cudaMalloc(&t.d_flags, static_cast<size_t>(nflags + 1) * sizeof(int));   // + item counter
+  if (err != cudaSuccess) {
+    cudaFree(t.d_items);
+    CUDA_TRY(e, err);
+  }
   // pageable source: the copy is staged before the call returns, so `items` may go out of scope
-  CUDA_TRY(e, cudaMemcpyAsync(lane->d_rdb_items, items.data(), items.size() * sizeof(RdbItem), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(e, cudaStreamSynchronize(st));
-  lane->rdb_n = N;
-  lane->rdb_h = H;
-  lane->rdb_w = W;
-  lane->rdb_gen = e->rdb_gen;
-  lane->rdb_nitems = static_cast<int>(items.size());
-  lane->rdb_nflags = nflags;
+  err = cudaMemcpyAsync(t.d_items, items.data(), items.size() * sizeof(RdbItem), cudaMemcpyHostToDevice, st);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+  if (err != cudaSuccess) {
+    cudaFree(t.d_items);
+    cudaFree(t.d_flags);
+    CUDA_TRY(e, err);
+  }
+  t.n = N;
+  t.h = H;
+  t.w = W;
+  t.gen = e->rdb_gen;
+  t.nitems = static_cast<int>(items.size());
+  t.nflags = nflags;
+  lane->rdb_tables.push_back(t);
+  lane->d_rdb_items = t.d_items;
+  lane->d_rdb_flags = t.d_flags;
+  lane->rdb_nitems = t.nitems;
+  lane->rdb_nflags = t.nflags;
   return B200SR_OK;
 }
 
@@ -951,8 +979,10 @@ int b200sr_create(const b200sr_model_desc* desc, int device, b200sr_engine** out
 
 static void free_lane(Lane* l) {
   if (l->ws) cudaFree(l->ws);
-  if (l->d_rdb_items) cudaFree(l->d_rdb_items);
-  if (l->d_rdb_flags) cudaFree(l->d_rdb_flags);
+  for (auto& t : l->rdb_tables) {
+    if (t.d_items) cudaFree(t.d_items);
+    if (t.d_flags) cudaFree(t.d_flags);
+  }
   if (l->dev_in) cudaFree(l->dev_in);
   if (l->dev_out) cudaFree(l->dev_out);
   if (l->pin_in) cudaFreeHost(l->pin_in);
@@ -1096,6 +1126,13 @@ static int enqueue_impl(b200sr_engine* e, Lane* lane, const void* src_dev_v, voi
   if ((Hp > h + pre_pad && h + pre_pad < 2) || (Wp > w + pre_pad && w + pre_pad < 2))
     return fail(e, B200SR_ERR_INVALID, "frame too small for reflect mod-padding");
   std::vector<Region> regions = plan_regions(e->desc.arch, scale, h, w, tile, tile_pad, pre_pad);
+  {  // one workspace allocation for the largest region (tile mode: six shapes per frame)
+    const int us = (e->desc.arch == B200SR_ARCH_RRDB && scale == 2) ? 2 : 1;
+    size_t need = 0;
+    for (const Region& R : regions) need = std::max(need, region_ws_bytes(e, n, R.rh / us, R.rw / us));
+    int rc = ensure_ws(e, lane, need, st);
+    if (rc) return rc;
+  }
   for (Region R : regions) {
     R.src = src_dev;
     R.dst = dst_dev;
