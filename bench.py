@@ -464,9 +464,33 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": 1.0 / cdt, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"one full 1280x720 frame (frame 0 of the timed batch), one pass of the fp32 "
                                           f"torch oracle: {cdt:.1f} s; no extrapolation"}
+    # ---- the PRODUCT scheduler over the same N GPUs (strong scaling of a fixed clip): rank 0 drives
+    # MultiGPUDistributor.distribute_frames with one persistent worker process per GPU; the other ranks have released
+    # their engines and wait.  (`--workload clip2000` runs the full 2000-frame clip the same way.)
+    plugin.clear_upsampler_cache()
+    del dev_in, dev_out
+    torch.cuda.empty_cache()
+    barrier()
+    if rank == 0 and args.sched_frames > 0:
+        try:
+            from tools.clip_bench import run_clip_job
+
+            line["product_scheduler"] = run_clip_job(world, args.sched_frames, batch=2, threads=3)
+        except Exception as e:  # the contract line must not depend on it
+            line["product_scheduler"] = {"error": f"{type(e).__name__}: {e}"}
+    if world > 1:
+        # host-side rendezvous (an NCCL barrier would park a spinning kernel on the GPUs the scheduler is using)
+        from datetime import timedelta
+
+        from torch.distributed import distributed_c10d as c10d
+
+        store = c10d._get_default_store()
+        if rank == 0:
+            store.set("b200sr_sched_done", "1")
+        else:
+            store.wait(["b200sr_sched_done"], timedelta(seconds=900))
     if rank == 0:
         print(json.dumps(line))
-    plugin.clear_upsampler_cache()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -483,6 +507,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="step", choices=["step", "clip2000"])
     ap.add_argument("--clip-frames", type=int, default=2000)
+    ap.add_argument("--sched-frames", type=int, default=-1,
+                    help="frames of the clip pushed through the product scheduler after the main measurement "
+                         "(default: 96 per GPU; 0 = skip)")
     ap.add_argument("--clip-batch", type=int, default=2, help="frames per engine call in the scheduler's workers")
     ap.add_argument("--clip-threads", type=int, default=3, help="runner threads per worker process")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -490,6 +517,8 @@ def main():
     args = ap.parse_args()
     global STREAMS
     STREAMS = args.streams
+    if args.sched_frames < 0:
+        args.sched_frames = 96 * max(1, int(os.environ.get("WORLD_SIZE", "1")))
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "clip2000":

@@ -74,9 +74,9 @@ class SyntheticClip:
         self._frames = None
 
 
-def run_clip(args) -> int:
-    if int(os.environ.get("RANK", "0")) != 0:     # launched under torchrun: one scheduler drives all GPUs
-        return 0
+def run_clip_job(n_gpus: int, frames: int, batch: int = 2, threads: int = 3, model: str = "RealESRGAN_x4plus") -> dict:
+    """One clip of `frames` synthetic 720p frames through MultiGPUDistributor.distribute_frames on the first `n_gpus`
+    GPUs (workers warmed by a short job first).  Returns the measurement as a dict."""
     import torch
 
     import framewright_b200  # noqa: F401
@@ -84,44 +84,50 @@ def run_clip(args) -> int:
     from framewright_b200.scheduler import ChecksumSink
 
     os.environ["B200SR_SYNTHETIC_WEIGHTS"] = "0"      # inherited by the worker processes (explicit opt-in)
-    model = "RealESRGAN_x4plus"
-    n_gpus = max(1, min(args.gpus, torch.cuda.device_count()))
+    n_gpus = max(1, min(n_gpus, torch.cuda.device_count()))
     gpus = mg.query_gpus()[:n_gpus]
     h, w = 720, 1280
-    d = mg.MultiGPUDistributor(gpus=gpus, strategy=mg.LoadBalanceStrategy.ROUND_ROBIN, workers_per_gpu=args.clip_threads - 1,
-                               batch=args.clip_batch, model_name=model, scale=4, tile=0)
+    d = mg.MultiGPUDistributor(gpus=gpus, strategy=mg.LoadBalanceStrategy.ROUND_ROBIN, workers_per_gpu=threads - 1,
+                               batch=batch, model_name=model, scale=4, tile=0)
     t_start = time.time()
     try:
         # warm-up job on the same clip (same seed): engines, workspaces, pinned pools and the workers' base frames
         warm = d.distribute_frames(SyntheticClip(8 * n_gpus, h, w, seed=4), None, None, sink=ChecksumSink())
         assert not warm.errors, warm.errors
         startup_s = time.time() - t_start
-        per_frame = []
         t0 = time.time()
-        res = d.distribute_frames(SyntheticClip(args.clip_frames, h, w, seed=4), None, None, sink=ChecksumSink(),
-                                  frame_callback=lambda i, name, ok, err, gpu: per_frame.append(time.time()))
+        res = d.distribute_frames(SyntheticClip(frames, h, w, seed=4), None, None, sink=ChecksumSink())
         dt = time.time() - t0
         rr = d.last_run
     finally:
         d.close()
     ok = res.total_frames
-    fps = ok / dt
-    checksum = int(sum(v[1] for v in rr.ok.values()) % (1 << 61))
+    return {"value": ok / dt, "unit": "frames/s", "n_gpus": n_gpus, "frames": frames, "frames_ok": ok,
+            "frames_failed": len(res.errors), "frames_per_gpu": {str(g): len(v) for g, v in res.frames_per_gpu.items()},
+            "stolen": rr.stolen, "retried": len(rr.retried), "wall_s": dt, "startup_s": startup_s,
+            "batch": batch, "threads_per_worker": threads,
+            "output_checksum": int(sum(v[1] for v in rr.ok.values()) % (1 << 61)),
+            "what": f"{model} x4 over a {frames}-frame synthetic 1280x720 clip through MultiGPUDistributor.distribute_frames "
+                    "(persistent worker process per GPU, contiguous shards + tail stealing, frames generated in the "
+                    "workers from seed + index, results copied to host memory)",
+            "timing": "parent wall clock, job submission -> last completion message; workers warm"}
+
+
+def run_clip(args) -> int:
+    if int(os.environ.get("RANK", "0")) != 0:     # launched under torchrun: one scheduler drives all GPUs
+        return 0
+    m = run_clip_job(args.gpus, args.clip_frames, batch=args.clip_batch, threads=args.clip_threads)
+    h, w = 720, 1280
     line = {
-        "metric": "frames_per_sec_rrdbnet_x4_720p", "value": fps, "unit": "frames/s", "n_gpus": n_gpus,
-        "steps": 1, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "metric": "frames_per_sec_rrdbnet_x4_720p", "value": m["value"], "unit": "frames/s", "n_gpus": m["n_gpus"],
+        "steps": 1, "warmup": 1, "ms_per_step": m["wall_s"] * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{model} x4 over a {args.clip_frames}-frame synthetic 1280x720 clip, untiled, through "
-                               "MultiGPUDistributor.distribute_frames (persistent worker per GPU, contiguous shards + "
-                               "tail stealing, frames generated in the workers from seed + index, results to host)",
-                   "frames": args.clip_frames, "batch": args.clip_batch, "threads_per_worker": args.clip_threads,
-                   "parallelism": f"frame-sharded x{n_gpus}, no collective"},
-        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": args.clip_frames * h * w * 3,
+        "config": {"workload": m["what"], "frames": args.clip_frames, "batch": args.clip_batch,
+                   "threads_per_worker": args.clip_threads, "parallelism": f"frame-sharded x{m['n_gpus']}, no collective"},
+        "e2e": {"value": m["value"], "unit": "frames/s", "h2d_bytes_per_step": args.clip_frames * h * w * 3,
                 "d2h_bytes_per_step": args.clip_frames * h * w * 3 * 16},
-        "frames_ok": ok, "frames_failed": len(res.errors), "frames_per_gpu": {str(g): len(v) for g, v in res.frames_per_gpu.items()},
-        "stolen": rr.stolen, "retried": len(rr.retried), "wall_s": dt, "startup_s": startup_s,
-        "timing": "parent wall clock, job submission -> last completion message; workers warm",
-        "output_checksum": checksum,
     }
+    line.update({k: m[k] for k in ("frames_ok", "frames_failed", "frames_per_gpu", "stolen", "retried", "wall_s",
+                                   "startup_s", "timing", "output_checksum")})
     print(json.dumps(line))
-    return 0 if ok == args.clip_frames else 1
+    return 0 if m["frames_ok"] == args.clip_frames else 1
