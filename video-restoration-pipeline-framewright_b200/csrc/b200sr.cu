@@ -35,6 +35,7 @@ struct Layer {
   bool fp16 = false;            // 16-bit format of this layer's inputs and weights (false = bf16)
   std::vector<float> w, b;      // host fp32 OIHW / bias
   uint8_t* d_wpack = nullptr;   // packed bf16 image (tensor-core layers)
+  uint8_t* d_wsub[4] = {nullptr, nullptr, nullptr, nullptr};   // conv_up1 / conv_up2: one image per sub-pixel phase (a, b)
   float* d_wfirst = nullptr;    // [9][cin][64] fp32 (first layer, CUDA-core kernel)
   std::vector<float> wfirst;    // the same on the host (3-channel first layer: passed as a kernel parameter)
   float* d_bias = nullptr;      // coutp floats
@@ -119,7 +120,7 @@ struct b200sr_engine {
   int opt_fused_rdb = 1;    // run each RDB as one persistent kernel (L2-resident intermediates)
   int opt_first_v1 = 0;     // input stage: 0 = constant-bank kernel (3 ch) / tiled kernel (12 ch); 1 = round-1 per-pixel
                             // kernel; 2 = tiled kernel for 3 ch too (all bit-identical; tests / A-B timing)
-  int opt_fold_up = 1;      // conv_up1/up2 read the nearest-2x upsampling through the duplicated-pixel TMA view
+  int opt_fold_up = 1;      // conv_up1/up2: 0 materialised upsampling, 1 duplicated-pixel TMA view, 2 sub-pixel phases
   int opt_rdb_stats = 0;    // dev: collect per-CTA cycle counters of the k-th fused launch of a forward pass (1-based)
   int rdb_gen = 0;          // bumped when a schedule option changes: lanes rebuild their work lists
   int stats_nitems = 0;
@@ -266,6 +267,27 @@ std::vector<uint8_t> pack_weights(const Layer& l) {
   return img;
 }
 
+// "nearest-2x upsample, then 3x3 conv" == four 2x2 convs on the low-resolution grid, one per output phase (a, b):
+// HR row 2y+a reads source rows {y-1, y, y} (a = 0) or {y, y, y+1} (a = 1) for ky = 0, 1, 2, so the taps that read the
+// same source row are summed (same for columns).  The 2x2 kernel is embedded in a 3x3 one -- (ky', kx') = position
+// relative to the centre -- whose unused row / column is zero and is never issued (ConvArgs::sub_*).
+std::vector<uint8_t> pack_subpixel_weights(const Layer& l, int a, int b) {
+  Layer t;
+  t.cin = l.cin;
+  t.cout = l.cout;
+  t.coutp = l.coutp;
+  t.fp16 = l.fp16;
+  t.w.assign(l.w.size(), 0.f);
+  const int vmap[2][3] = {{0, 1, 1}, {1, 1, 2}};   // ky (or kx) -> ky' for phase 0 / 1
+  for (int co = 0; co < l.cout; ++co)
+    for (int ci = 0; ci < l.cin; ++ci) {
+      const size_t base = (static_cast<size_t>(co) * l.cin + ci) * 9;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) t.w[base + vmap[a][ky] * 3 + vmap[b][kx]] += l.w[base + ky * 3 + kx];
+    }
+  return pack_weights(t);
+}
+
 template <int COUT, int EPI>
 int launch_conv_inst(b200sr_engine* e, Lane* lane, const CUtensorMap& amap, const ConvArgs& a, cudaStream_t st,
                      int pcls, double flops) {
@@ -329,10 +351,11 @@ int launch_conv(b200sr_engine* e, Lane* lane, const Layer& l, int epi, const Con
   a.xtiles = (io.W + 127) / 128;
   a.ytiles = (io.H + a.TH - 1) / a.TH;
   a.ntiles = a.xtiles * a.ytiles * io.N;
-  a.wpack = l.d_wpack;
+  a.wpack = a.sub ? l.d_wsub[a.sub_a * 2 + a.sub_b] : l.d_wpack;
   a.bias = l.d_bias;
   a.in_fp16 = l.fp16 ? 1 : 0;
-  // algorithmic FLOPs of this launch: true channel counts, every output pixel, 9 taps
+  // algorithmic FLOPs of this launch: true channel counts, every output pixel, 9 taps (a sub-pixel phase launch
+  // produces N x H x W of the 4 N H W output pixels of the upsample + conv it implements, with 4 issued taps each)
   const double fl = 2.0 * 9.0 * l.cin * l.cout * static_cast<double>(io.N) * io.H * io.W;
   switch (l.coutp * 16 + epi) {
     case 32 * 16 + EPI_ACT_BF16: return launch_conv_inst<32, EPI_ACT_BF16>(e, lane, amap, a, st, PC_CONV32_ACT, fl);
@@ -852,30 +875,41 @@ int run_region(b200sr_engine* e, Lane* lane, const Region& R, cudaStream_t st) {
         rc = run_upsample(e, lane, U0f, U1, n, H, W, st);
         if (rc) return rc;
       }
-      {  // conv_up1 + lrelu
-        ConvIO io{e->opt_fold_up ? static_cast<const void*>(U0f) : U1, 64, n, 2 * H, 2 * W, 0, e->opt_fold_up};
+      // conv_up1 / conv_up2 (+ lrelu).  fold_up 2: four sub-pixel phase launches on the low-resolution grid (2.25x
+      // fewer MACs: the taps that read the same source pixel are pre-summed); 1: one launch through the
+      // duplicated-pixel TMA view; 0: on the materialised upsampling.
+      auto conv_up = [&](const Layer& l, const void* lr, const void* up, __nv_bfloat16* dstt, int h, int w) -> int {
         ConvArgs a = tb;
         a.slope = 0.2f;
-        a.out = U2;
+        a.out = dstt;
         a.out_pitch = 64;
         a.out_fp16 = 1;
-        rc = launch_conv(e, lane, l_up1, EPI_ACT_BF16, io, a, st);
-        if (rc) return rc;
-      }
+        if (e->opt_fold_up == 2) {
+          ConvIO io{lr, 64, n, h, w};
+          for (int ph = 0; ph < 4; ++ph) {
+            a.sub = 1;
+            a.sub_a = ph >> 1;
+            a.sub_b = ph & 1;
+            a.sub_vlo = a.sub_a ? 0 : 1;
+            a.sub_vhi = a.sub_a ? 1 : 2;
+            a.sub_dlo = a.sub_b ? 1 : 0;
+            a.sub_dhi = a.sub_b ? 2 : 1;
+            int r = launch_conv(e, lane, l, EPI_ACT_BF16, io, a, st);
+            if (r) return r;
+          }
+          return B200SR_OK;
+        }
+        ConvIO io{e->opt_fold_up ? lr : up, 64, n, 2 * h, 2 * w, 0, e->opt_fold_up ? 1 : 0};
+        return launch_conv(e, lane, l, EPI_ACT_BF16, io, a, st);
+      };
+      rc = conv_up(l_up1, U0f, U1, U2, H, W);
+      if (rc) return rc;
       if (!e->opt_fold_up) {
         rc = run_upsample(e, lane, U2, U3, n, 2 * H, 2 * W, st);
         if (rc) return rc;
       }
-      {  // conv_up2 + lrelu
-        ConvIO io{e->opt_fold_up ? U2 : U3, 64, n, 4 * H, 4 * W, 0, e->opt_fold_up};
-        ConvArgs a = tb;
-        a.slope = 0.2f;
-        a.out = U4;
-        a.out_pitch = 64;
-        a.out_fp16 = 1;
-        rc = launch_conv(e, lane, l_up2, EPI_ACT_BF16, io, a, st);
-        if (rc) return rc;
-      }
+      rc = conv_up(l_up2, U2, U3, U4, 2 * H, 2 * W);
+      if (rc) return rc;
       {  // conv_hr + lrelu
         ConvIO io{U4, 64, n, 4 * H, 4 * W};
         ConvArgs a = tb;
@@ -997,6 +1031,8 @@ void b200sr_destroy(b200sr_engine* e) {
   cudaDeviceSynchronize();
   for (auto& l : e->layers) {
     if (l.d_wpack) cudaFree(l.d_wpack);
+    for (auto* p : l.d_wsub)
+      if (p) cudaFree(p);
     if (l.d_wfirst) cudaFree(l.d_wfirst);
     if (l.d_bias) cudaFree(l.d_bias);
   }
@@ -1068,6 +1104,14 @@ int b200sr_finalize(b200sr_engine* e) {
       std::vector<uint8_t> img = pack_weights(l);
       if (!l.d_wpack) CUDA_TRY(e, cudaMalloc(&l.d_wpack, img.size()));
       CUDA_TRY(e, cudaMemcpy(l.d_wpack, img.data(), img.size(), cudaMemcpyHostToDevice));
+      const size_t nl = e->layers.size();
+      if (e->desc.arch == B200SR_ARCH_RRDB && (i == nl - 4 || i == nl - 3)) {   // conv_up1, conv_up2
+        for (int ph = 0; ph < 4; ++ph) {
+          std::vector<uint8_t> simg = pack_subpixel_weights(l, ph >> 1, ph & 1);
+          if (!l.d_wsub[ph]) CUDA_TRY(e, cudaMalloc(&l.d_wsub[ph], simg.size()));
+          CUDA_TRY(e, cudaMemcpy(l.d_wsub[ph], simg.data(), simg.size(), cudaMemcpyHostToDevice));
+        }
+      }
     }
   }
   for (size_t i = 0; i < e->prelu_host.size(); ++i) {

@@ -60,6 +60,12 @@ struct ConvArgs {
   int in_up2;             // the input is the nearest-2x upsampling of a tensor of half this conv's H and W, read
                           // through the duplicated-pixel TMA view (tmap.h::tmap_encode_act_up2): box = 66 source
                           // pixels = 132 rows starting at x0 - 2, so every tap view starts one row later
+  int sub;                // sub-pixel phase of "nearest-2x upsample, then this conv": the conv runs on the LOW-resolution
+                          // grid (N, H, W are its dims) with the 2x2 taps of phase (sub_a, sub_b) -- the weights that
+                          // read the same source pixel are pre-summed and embedded in a 3x3 image whose unused ky / kx
+                          // blocks are never issued: vertical blocks [sub_vlo, sub_vhi], dx tiles [sub_dlo, sub_dhi] --
+                          // and output pixel (y, x) lands at (2 y + sub_a, 2 x + sub_b) of the 2H x 2W tensor `out`
+  int sub_a, sub_b, sub_vlo, sub_vhi, sub_dlo, sub_dhi;
   int in_fp16;            // A (activations) and B (weights) are fp16 instead of bf16
   int out_fp16;           // 16-bit output tensor is fp16 instead of bf16
   __nv_bfloat16* out;     // 16-bit NHWC destination (bf16 or fp16 per out_fp16)
@@ -359,7 +365,8 @@ __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* s
       float v = acc[c] + s_bias[c];
       acc[c] = v > 0.f ? v : v * a.slope;
     }
-    store_bf16_row<COUT>(a.out + pix * a.out_pitch + a.out_choff, acc, a.out_fp16);
+    const size_t opix = a.sub ? (static_cast<size_t>(n) * (2 * a.H) + (2 * y + a.sub_a)) * (2 * a.W) + (2 * x + a.sub_b) : pix;
+    store_bf16_row<COUT>(a.out + opix * a.out_pitch + a.out_choff, acc, a.out_fp16);
   } else if constexpr (EPI == EPI_PRELU_BF16) {
 #pragma unroll
     for (int c = 0; c < COUT; ++c) {
@@ -537,6 +544,54 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
         const bool last_chunk = (c == args.nchunks - 1);
         mbar_wait(&bar_wfull[wb], wphase);
         const uint64_t bdesc_w = bdesc0 + static_cast<uint64_t>((wb * Cfg::WCHUNK_BYTES) >> 4);
+        if (args.sub) {
+          // sub-pixel phase: vertical blocks [vlo, vhi] and dx tiles [dlo, dhi] only (the other weights are zero and
+          // are never issued).  Accumulator row R is first touched by input row R + 1 - vhi and complete after input
+          // row R + 1 - vlo.
+          const int vlo = args.sub_vlo, vhi = args.sub_vhi, dlo = args.sub_dlo, dhi = args.sub_dhi;
+          for (int y = -1; y <= TH; ++y) {
+            int blk_lo = (y < 1) ? (1 - y) : 0;
+            int blk_hi = (TH - y < 2) ? (TH - y) : 2;
+            blk_lo = blk_lo > vlo ? blk_lo : vlo;
+            blk_hi = blk_hi < vhi ? blk_hi : vhi;
+            const int nblk = blk_hi - blk_lo + 1;
+            const bool new_row = first_chunk && nblk >= 1 && blk_hi == vhi;   // row y-1+vhi touched for the first time
+            if (new_row) mbar_wait(&bar_rempty[y - 1 + vhi], rparity);
+            mbar_wait(&bar_full[stage], phase);
+            tc_fence_after();
+            const uint32_t dcol = tmem_base + static_cast<uint32_t>((y - 1 + blk_lo) * COUT);
+            const uint64_t ad0 = adesc0 + static_cast<uint64_t>((stage * Cfg::A_STAGE_BYTES) >> 4);
+            const uint64_t bd0 = bdesc_w + static_cast<uint64_t>((blk_lo * COUT * 128) >> 4);
+            const uint32_t idesc_n = nblk == 3 ? idesc3 : (nblk == 2 ? idesc2 : idesc1);
+            if (elect_one_sync()) {
+              if (nblk >= 1) {
+                bool first = true;
+                for (int dx = dlo; dx <= dhi; ++dx)
+                  for (int k = 0; k < ks; ++k) {
+                    const uint64_t ad = ad0 + static_cast<uint64_t>((dx * 128 + k * 32) >> 4);
+                    const uint64_t bd = bd0 + static_cast<uint64_t>((dx * Cfg::WTILE_BYTES + k * 32) >> 4);
+                    if (first && new_row) {
+                      if (nblk > 1) umma_bf16(dcol, ad, bd, nblk == 3 ? idesc2 : idesc1, 1);
+                      umma_bf16(dcol + (nblk - 1) * COUT, ad, bd + static_cast<uint64_t>(((nblk - 1) * COUT * 128) >> 4),
+                                idesc1, 0);
+                    } else {
+                      umma_bf16(dcol, ad, bd, idesc_n, 1);
+                    }
+                    first = false;
+                  }
+              }
+              umma_commit(&bar_empty[stage]);
+              const int R = y - 1 + vlo;                                   // the row this input row completes
+              if (last_chunk && R >= 0 && R < TH) umma_commit(&bar_rfull[R]);
+              if (y == TH) umma_commit(&bar_wempty[wb]);
+            }
+            __syncwarp();
+            if (++stage == Cfg::NSTAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        } else {
         for (int y = -1; y <= TH; ++y) {
           const int blk_lo = (y < 1) ? (1 - y) : 0;        // output row y-1+blk must be >= 0
           const int blk_hi = (TH - y < 2) ? (TH - y) : 2;  // and < TH
@@ -583,6 +638,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
             stage = 0;
             phase ^= 1;
           }
+        }
         }
         if (++wb == Cfg::NWBUF) {
           wb = 0;
