@@ -56,3 +56,16 @@ class CountingSource:
 
     def load(self, i):
         return np.full((self.h, self.w, 3), i % 251, np.uint8)
+
+
+class HangingUpsampler(FakeUpsampler):
+    """GPU 1 never returns (a hung device): the parent must give up on it."""
+
+    def enhance_batch(self, frames, out=None):
+        if self.gpu_id == 1:
+            time.sleep(3600)
+        return super().enhance_batch(frames, out)
+
+
+def hanging_engine(cfg):
+    return HangingUpsampler(cfg)

@@ -197,3 +197,20 @@ def test_distributor_product_path_over_the_pool(tmp_path):
         assert res2.total_frames == 4 and {g: p.pid for g, p in d._pool._procs.items()} == pids
     finally:
         d.close()
+
+
+def test_a_hung_worker_is_terminated_after_the_stall_timeout():
+    """A worker that is alive but never answers (hung GPU): after `stall_timeout` it is terminated, its frames are
+    retried on the other GPU, the job completes."""
+    import framewright_b200  # noqa: F401
+    from framewright_b200.scheduler import ChecksumSink, SchedulerPool
+
+    from sched_helpers import hanging_engine
+
+    p = SchedulerPool([0, 1], workers_per_gpu=1, start_timeout=120, stall_timeout=3.0)
+    try:
+        res = p.run(CountingSource(12), ChecksumSink(), dict(CFG, tile_pad=25), batch=2, engine_factory=hanging_engine)
+        assert sorted(res.ok) == list(range(12)) and not res.errors
+        assert res.dead_gpus == [1] and res.retried and p.alive_gpus() == [0]
+    finally:
+        p.close()

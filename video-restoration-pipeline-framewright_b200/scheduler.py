@@ -517,11 +517,15 @@ class RunResult:
 class SchedulerPool:
     """One persistent worker process per GPU.  `run` pushes one job (a frame source + sink) through them."""
 
-    def __init__(self, gpu_ids: Sequence[int], workers_per_gpu: int = 3, start_timeout: float = 300.0):
+    def __init__(self, gpu_ids: Sequence[int], workers_per_gpu: int = 3, start_timeout: float = 300.0,
+                 stall_timeout: float = 900.0):
         if not gpu_ids:
             raise ValueError("SchedulerPool needs at least one GPU id")
         self.gpu_ids = [int(g) for g in gpu_ids]
         self.workers_per_gpu = max(1, int(workers_per_gpu))
+        # a worker that is alive but silent for this long while it holds frames (a hung GPU) is terminated and treated
+        # like a dead one (the reference bounds every future with a timeout, utils/multi_gpu.py:741)
+        self.stall_timeout = float(stall_timeout)
         self._ctx = mp.get_context("spawn")
         self._results = self._ctx.Queue()
         self._retry = self._ctx.Queue()
@@ -637,11 +641,22 @@ class SchedulerPool:
                 else:
                     final(i, False, err, gpu, None)
 
+            last_heard = {g: time.time() for g in self.gpu_ids}
             while done_count < n:
                 try:
                     m = self._results.get(timeout=0.25)
                 except queue_mod.Empty:
                     m = None
+                if m is not None and len(m) > 2 and m[1] == job_id and m[0] in ("claim", "worker_error"):
+                    last_heard[m[2]] = time.time()
+                elif m is not None and m[0] == "done" and m[1] == job_id:
+                    last_heard[m[5]] = time.time()
+                for g, p in self._procs.items():   # hung worker: alive, holding frames, silent for too long
+                    if (g not in dead_seen and p.is_alive() and time.time() - last_heard[g] > self.stall_timeout
+                            and (in_flight[g] or (g in shard_of_gpu and self._claims.held_by(shard_of_gpu[g])))):
+                        logger.error("worker for GPU %s is silent for %.0f s: terminating it", g, self.stall_timeout)
+                        p.terminate()
+                        p.join(timeout=10)
                 if m is not None and len(m) > 1 and m[1] == job_id:
                     if m[0] == "claim":
                         in_flight[m[2]].update(i for i in m[3] if i not in finished)
