@@ -286,7 +286,10 @@ __device__ __forceinline__ float norm_sample(float x, float d, float rcp) {
 // Two pixels per thread (lane l of a warp owns pixels base + l and base + 32 + l), 16 output channels per pass: every
 // uniform weight pair feeds two FFMA2s, and 4 x 27 x 8 x 2 = 1728 FFMA2 + 432 LDCU.128 per thread replace the
 // 2 x (864 + 661) of the one-pixel form.
-__global__ void __launch_bounds__(128, 4) first_conv3_const_kernel(const FirstArgs a, const __grid_constant__ FirstWeights3 cw) {
+#ifndef B200SR_FIRST_MINBLOCKS
+#define B200SR_FIRST_MINBLOCKS 5     // 5 blocks / SM (<= 102 registers): 0.62 ms against 0.715 at 4 (4 x 720p, same box)
+#endif
+__global__ void __launch_bounds__(128, B200SR_FIRST_MINBLOCKS) first_conv3_const_kernel(const FirstArgs a, const __grid_constant__ FirstWeights3 cw) {
   const int xb = blockIdx.x * 256 + (threadIdx.x >> 5) * 64 + (threadIdx.x & 31);
   const int y = blockIdx.y;
   const int n = blockIdx.z;
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(128, 4) first_conv3_const_kernel(const FirstAr
         }
       }
   }
-#pragma unroll
+#pragma unroll 1                             // (rolled: the body is 432 FFMA2 long; unrolled x4 it thrashes the instruction cache)
   for (int qd = 0; qd < 4; ++qd) {          // channels [16 qd, 16 qd + 16)
     // packed fp32 FMAs (FFMA2: two IEEE fma.rn per instruction -- same bits as scalar fmaf): accumulator pairs of
     // adjacent channels, the input value broadcast, the weight pair from a uniform register
