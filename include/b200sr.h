@@ -109,6 +109,7 @@ int b200sr_last_launch_count(const b200sr_engine* e);
 /* Debug / measurement hooks (not part of the reference surface).
  * Options: "fused_rdb" (1: one persistent kernel per residual dense block; 0: five per-conv launches, same bytes),
  * "fold_up" (1: conv_up1/up2 read the nearest-2x upsampling through the duplicated-pixel TMA view; 0: materialise it),
+ * "w_resident" (1: convs with Cin <= 64 load their weights once per CTA and use the space for more activation stages),
  * "profile" (1: CUDA events around every launch, read with b200sr_get_profile), "force_th", "max_ctas",
  * "lanes" (host-buffer lanes, default 2), "host_chunk" (frames per lane job, 0 = auto), "ws_limit_mb" (tests: refuse
  * larger workspaces with B200SR_ERR_OOM),

@@ -74,8 +74,6 @@ def variant_flags(name: str):
         flags.append("-DB200SR_RDB_CTAS=2")
     if "rdb1" in name:
         flags.append("-DB200SR_RDB_CTAS=1")
-    if "fc4" in name:
-        flags.append("-DB200SR_FIRST_MINBLOCKS=4")
     return flags
 
 

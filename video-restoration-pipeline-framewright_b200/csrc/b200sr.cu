@@ -20,6 +20,7 @@
 
 #include "../../include/b200sr.h"
 #include "conv3x3_tc.cuh"
+#include "conv3x3_sc.cuh"
 #include "pointwise.cuh"
 #include "rdb_fused.cuh"
 #include "tmap.h"
@@ -36,6 +37,7 @@ struct Layer {
   std::vector<float> w, b;      // host fp32 OIHW / bias
   uint8_t* d_wpack = nullptr;   // packed bf16 image (tensor-core layers)
   uint8_t* d_wsub[4] = {nullptr, nullptr, nullptr, nullptr};   // conv_up1 / conv_up2: one image per sub-pixel phase (a, b)
+  uint8_t* d_wlast9 = nullptr;  // conv_last: kx taps stacked on N (conv3x3_sc.cuh, EPI_LAST9_U8)
   float* d_wfirst = nullptr;    // [9][cin][64] fp32 (first layer, CUDA-core kernel)
   std::vector<float> wfirst;    // the same on the host (3-channel first layer: passed as a kernel parameter)
   float* d_bias = nullptr;      // coutp floats
@@ -120,6 +122,10 @@ struct b200sr_engine {
   int opt_fused_rdb = 1;    // run each RDB as one persistent kernel (L2-resident intermediates)
   int opt_first_v1 = 0;     // input stage: 0 = constant-bank kernel (3 ch) / tiled kernel (12 ch); 1 = round-1 per-pixel
                             // kernel; 2 = tiled kernel for 3 ch too (all bit-identical; tests / A-B timing)
+  int opt_pair = 1;         // single-chunk convs through conv3x3_sc_kernel (resident weights, row-pair stages)
+  int opt_last9 = 1;        // conv_last with the kx taps stacked on N (needs opt_pair)
+  int opt_abl = 0;          // dev: timing ablations of the per-conv kernel (ConvArgs::abl); results are wrong when set
+  int opt_w_resident = 1;   // single-chunk convs keep their weights resident in shared memory (more activation stages)
   int opt_fold_up = 1;      // conv_up1/up2: 0 materialised upsampling, 1 duplicated-pixel TMA view, 2 sub-pixel phases
   int opt_rdb_stats = 0;    // dev: collect per-CTA cycle counters of the k-th fused launch of a forward pass (1-based)
   int rdb_gen = 0;          // bumped when a schedule option changes: lanes rebuild their work lists
@@ -288,6 +294,46 @@ std::vector<uint8_t> pack_subpixel_weights(const Layer& l, int a, int b) {
   return pack_weights(t);
 }
 
+// conv_last (64 -> 3) with the kx taps stacked on N: one dx tile whose ky block b holds rows [kx * 8 + co] (co < 3),
+// 32 rows per block (conv3x3_sc.cuh, EPI_LAST9_U8).
+std::vector<uint8_t> pack_weights_last9(const Layer& l) {
+  const size_t tile_bytes = static_cast<size_t>(3) * 32 * 128;
+  std::vector<uint8_t> img(tile_bytes, 0);
+  for (int blk = 0; blk < 3; ++blk) {
+    const int ky = 2 - blk;
+    for (int kx = 0; kx < 3; ++kx)
+      for (int co = 0; co < l.cout; ++co) {
+        const int r = blk * 32 + kx * 8 + co;
+        for (int j = 0; j < 64 && j < l.cin; ++j) {
+          const float v = l.w[((static_cast<size_t>(co) * l.cin + j) * 3 + ky) * 3 + kx];
+          uint32_t off = static_cast<uint32_t>(r) * 128 + (j / 8) * 16 + (j % 8) * 2;
+          off ^= ((off >> 7) & 7u) << 4;
+          const uint16_t h = l.fp16 ? f2h(v) : f2bf(v);
+          memcpy(img.data() + off, &h, 2);
+        }
+      }
+  }
+  return img;
+}
+
+template <int COUT, int EPI>
+int launch_sc_inst(b200sr_engine* e, Lane* lane, const CUtensorMap& amap, const ConvArgs& a, cudaStream_t st,
+                   int pcls, double flops) {
+  using Cfg = ScCfg<COUT, EPI>;
+  ProfScope prof_scope(e, pcls, flops, st);
+  static bool attr_done[16] = {};
+  auto kern = conv3x3_sc_kernel<COUT, EPI>;
+  if (!attr_done[e->device & 15]) {
+    CUDA_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done[e->device & 15] = true;
+  }
+  int grid = std::min(a.ntiles, e->opt_max_ctas > 0 ? e->opt_max_ctas : e->num_sms * ConvCfg<COUT>::CTAS_PER_SM);
+  kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>>(amap, a);
+  CUDA_TRY(e, cudaGetLastError());
+  lane->launches++;
+  return B200SR_OK;
+}
+
 template <int COUT, int EPI>
 int launch_conv_inst(b200sr_engine* e, Lane* lane, const CUtensorMap& amap, const ConvArgs& a, cudaStream_t st,
                      int pcls, double flops) {
@@ -307,10 +353,10 @@ int launch_conv_inst(b200sr_engine* e, Lane* lane, const CUtensorMap& amap, cons
 }
 
 // Rows per tile: fill the 512 TMEM columns unless a smaller TH balances the waves better.
-int choose_th(const b200sr_engine* e, int coutp, int N, int H, int W) {
+int choose_th(const b200sr_engine* e, int coutp, int N, int H, int W, int xpitch = 128) {
   const int maxth = (512 / B200SR_CTAS_PER_SM) / coutp;
   if (e->opt_force_th > 0) return std::min(e->opt_force_th, maxth);
-  const int xt = (W + 127) / 128;
+  const int xt = (W + xpitch - 1) / xpitch;
   const int slots = e->opt_max_ctas > 0 ? e->opt_max_ctas : e->num_sms * B200SR_CTAS_PER_SM;
   double best = 1e30;
   int best_th = maxth;
@@ -347,6 +393,8 @@ int launch_conv(b200sr_engine* e, Lane* lane, const Layer& l, int epi, const Con
   a.in_up2 = io.up2;
   a.nchunks = (l.cin + 63) / 64;
   a.last_ksteps = (l.cin % 64 == 32) ? 2 : 4;
+  a.w_resident = (a.nchunks == 1 && e->opt_w_resident) ? 1 : 0;
+  a.abl = e->opt_abl;
   a.TH = choose_th(e, l.coutp, io.N, io.H, io.W);
   a.xtiles = (io.W + 127) / 128;
   a.ytiles = (io.H + a.TH - 1) / a.TH;
@@ -357,6 +405,25 @@ int launch_conv(b200sr_engine* e, Lane* lane, const Layer& l, int epi, const Con
   // algorithmic FLOPs of this launch: true channel counts, every output pixel, 9 taps (a sub-pixel phase launch
   // produces N x H x W of the 4 N H W output pixels of the upsample + conv it implements, with 4 issued taps each)
   const double fl = 2.0 * 9.0 * l.cin * l.cout * static_cast<double>(io.N) * io.H * io.W;
+  if (a.nchunks == 1 && !a.sub && e->opt_pair && l.cin == 64) {
+    // product path of every single-chunk conv: resident weights, row-pair stages (conv3x3_sc.cuh)
+    if (epi == EPI_LAST_U8 && e->opt_last9 && l.d_wlast9 && B200SR_CTAS_PER_SM == 1) {
+      a.wpack = l.d_wlast9;
+      a.TH = choose_th(e, 32, io.N, io.H, io.W, 126);
+      a.xtiles = (io.W + 125) / 126;
+      a.ytiles = (io.H + a.TH - 1) / a.TH;
+      a.ntiles = a.xtiles * a.ytiles * io.N;
+      return launch_sc_inst<32, EPI_LAST9_U8>(e, lane, amap, a, st, PC_CONV16_LAST, fl);
+    }
+    switch (l.coutp * 16 + epi) {
+      case 64 * 16 + EPI_ACT_BF16: return launch_sc_inst<64, EPI_ACT_BF16>(e, lane, amap, a, st, PC_CONV64_ACT, fl);
+      case 64 * 16 + EPI_PRELU_BF16: return launch_sc_inst<64, EPI_PRELU_BF16>(e, lane, amap, a, st, PC_CONV64_PRELU, fl);
+      case 64 * 16 + EPI_ADD_F32: return launch_sc_inst<64, EPI_ADD_F32>(e, lane, amap, a, st, PC_CONV64_ADD, fl);
+      case 16 * 16 + EPI_LAST_U8: return launch_sc_inst<16, EPI_LAST_U8>(e, lane, amap, a, st, PC_CONV16_LAST, fl);
+      case 48 * 16 + EPI_SRVGG_LAST: return launch_sc_inst<48, EPI_SRVGG_LAST>(e, lane, amap, a, st, PC_CONV48_SRVGG_LAST, fl);
+      default: break;   // (Cout = 32 single-chunk convs: RDB conv1 through the per-conv path, tests only)
+    }
+  }
   switch (l.coutp * 16 + epi) {
     case 32 * 16 + EPI_ACT_BF16: return launch_conv_inst<32, EPI_ACT_BF16>(e, lane, amap, a, st, PC_CONV32_ACT, fl);
     case 64 * 16 + EPI_ACT_BF16: return launch_conv_inst<64, EPI_ACT_BF16>(e, lane, amap, a, st, PC_CONV64_ACT, fl);
@@ -673,8 +740,7 @@ int run_first(b200sr_engine* e, Lane* lane, const Region& R, int s, int H, int W
       cw.p[c] = prelu ? e->prelu_host[0][c] : 1.f;
     }
     cw.has_prelu = prelu ? 1 : 0;
-    dim3 grid((W + 255) / 256, H, R.n);   // 128 threads x 2 pixels
-    first_conv3_const_kernel<<<grid, 128, 0, st>>>(a, cw);
+    first_conv3_const_kernel<<<dim3((W + 127) / 128, H, R.n), 128, 0, st>>>(a, cw);   // one pixel per thread
   } else if (l.cin == 3) {
     using T = FirstTiled<3>;
     dim3 grid((W + 127) / 128, (H + T::ROWS - 1) / T::ROWS, R.n);
@@ -1034,6 +1100,7 @@ void b200sr_destroy(b200sr_engine* e) {
     for (auto* p : l.d_wsub)
       if (p) cudaFree(p);
     if (l.d_wfirst) cudaFree(l.d_wfirst);
+    if (l.d_wlast9) cudaFree(l.d_wlast9);
     if (l.d_bias) cudaFree(l.d_bias);
   }
   for (auto* p : e->prelu_dev)
@@ -1105,6 +1172,11 @@ int b200sr_finalize(b200sr_engine* e) {
       if (!l.d_wpack) CUDA_TRY(e, cudaMalloc(&l.d_wpack, img.size()));
       CUDA_TRY(e, cudaMemcpy(l.d_wpack, img.data(), img.size(), cudaMemcpyHostToDevice));
       const size_t nl = e->layers.size();
+      if (e->desc.arch == B200SR_ARCH_RRDB && i == nl - 1) {   // conv_last: stacked-kx image
+        std::vector<uint8_t> simg = pack_weights_last9(l);
+        if (!l.d_wlast9) CUDA_TRY(e, cudaMalloc(&l.d_wlast9, simg.size()));
+        CUDA_TRY(e, cudaMemcpy(l.d_wlast9, simg.data(), simg.size(), cudaMemcpyHostToDevice));
+      }
       if (e->desc.arch == B200SR_ARCH_RRDB && (i == nl - 4 || i == nl - 3)) {   // conv_up1, conv_up2
         for (int ph = 0; ph < 4; ++ph) {
           std::vector<uint8_t> simg = pack_subpixel_weights(l, ph >> 1, ph & 1);
@@ -1452,6 +1524,22 @@ int b200sr_set_option(b200sr_engine* e, const char* key, int value) {
   }
   if (!strcmp(key, "fold_up")) {
     e->opt_fold_up = value;
+    return B200SR_OK;
+  }
+  if (!strcmp(key, "pair")) {
+    e->opt_pair = value;
+    return B200SR_OK;
+  }
+  if (!strcmp(key, "last9")) {
+    e->opt_last9 = value;
+    return B200SR_OK;
+  }
+  if (!strcmp(key, "abl")) {
+    e->opt_abl = value;
+    return B200SR_OK;
+  }
+  if (!strcmp(key, "w_resident")) {
+    e->opt_w_resident = value;
     return B200SR_OK;
   }
   if (!strcmp(key, "lanes")) {   // host-buffer lanes (streams + workspaces); takes effect for lanes not yet created

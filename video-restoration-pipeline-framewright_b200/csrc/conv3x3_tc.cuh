@@ -66,6 +66,11 @@ struct ConvArgs {
                           // blocks are never issued: vertical blocks [sub_vlo, sub_vhi], dx tiles [sub_dlo, sub_dhi] --
                           // and output pixel (y, x) lands at (2 y + sub_a, 2 x + sub_b) of the 2H x 2W tensor `out`
   int sub_a, sub_b, sub_vlo, sub_vhi, sub_dlo, sub_dhi;
+  int w_resident;         // single-chunk conv (Cin <= 64): the weight chunk is loaded ONCE per CTA and stays in shared
+                          // memory; the second weight buffer's space becomes extra activation stages (more bytes in
+                          // flight per SM: the HR-tail convs are bound by DRAM latency x bytes in flight)
+  int abl;                // timing ablations (dev option "abl", results are WRONG when set): 1 = no epilogue stores,
+                          // 2 = no MMAs issued (commits only), 4 = no TMA activation loads
   int in_fp16;            // A (activations) and B (weights) are fp16 instead of bf16
   int out_fp16;           // 16-bit output tensor is fp16 instead of bf16
   __nv_bfloat16* out;     // 16-bit NHWC destination (bf16 or fp16 per out_fp16)
@@ -109,7 +114,14 @@ struct ConvCfg {
   static constexpr int NSTAGES_FIT = (SMEM_BUDGET - NWBUF * WCHUNK_BYTES) / A_STAGE_BYTES;
   static constexpr int NSTAGES = NSTAGES_FIT > 6 ? 6 : NSTAGES_FIT;
   static_assert(NSTAGES >= 2, "not enough shared memory for two activation stages");
-  static constexpr int SMEM_BYTES = NWBUF * WCHUNK_BYTES + NSTAGES * A_STAGE_BYTES + 1024 /*align slack*/;
+  // resident-weights mode (ConvArgs::w_resident): one weight buffer, everything else is activation stages
+  static constexpr int MAXSTAGES = 12;
+  static constexpr int NSTAGES_RES_FIT = (SMEM_BUDGET - WCHUNK_BYTES) / A_STAGE_BYTES;
+  static constexpr int NSTAGES_RES = NSTAGES_RES_FIT > MAXSTAGES ? MAXSTAGES : NSTAGES_RES_FIT;
+  static_assert(NSTAGES_RES >= NSTAGES && NSTAGES <= MAXSTAGES, "stage counts");
+  static constexpr int SMEM_BYTES_DB = NWBUF * WCHUNK_BYTES + NSTAGES * A_STAGE_BYTES + 1024 /*align slack*/;
+  static constexpr int SMEM_BYTES_RES = WCHUNK_BYTES + NSTAGES_RES * A_STAGE_BYTES + 1024;
+  static constexpr int SMEM_BYTES = SMEM_BYTES_DB > SMEM_BYTES_RES ? SMEM_BYTES_DB : SMEM_BYTES_RES;
   static constexpr int NEPI_WARPS = CTAS_PER_SM == 1 ? 8 : 4;   // epilogue warps (multiple of 4)
   static constexpr int NTHREADS = 32 * (2 + NEPI_WARPS);        // warp 0 TMA, warp 1 MMA, rest epilogue
 };
@@ -409,6 +421,33 @@ __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* s
     static_assert(EPI == EPI_SRVGG_LAST && COUT == 48, "SRVGG tail needs 48 channels");
     const float4 in = *reinterpret_cast<const float4*>(a.fadd + pix * 4);  // normalised RGB of this LR pixel
     const float base[3] = {in.x, in.y, in.z};
+    // The pixel's 4 x 4 HR block: 12 contiguous bytes per HR row.  When the whole block lies inside the crop window
+    // (always, except at tile-mode crop borders) and samples are 8-bit, each HR row is three aligned 32-bit stores
+    // instead of twelve byte stores (the byte form made this epilogue half of the kernel's time); the byte offset
+    // 3 * (dst_x0 - crop_x0 + 4 x) is a multiple of 4 whenever dst_x0 - crop_x0 is a multiple of 4 (it is 4 * pad).
+    const int cy0 = y * 4 - a.crop_y0, cx0 = x * 4 - a.crop_x0;
+    const bool whole = !a.dst16 && cy0 >= 0 && cy0 + 3 < a.crop_h && cx0 >= 0 && cx0 + 3 < a.crop_w &&
+                       (((a.dst_x0 + cx0) * 3) & 3) == 0 && ((a.dst_w * 3) & 3) == 0 &&
+                       (reinterpret_cast<uintptr_t>(a.dst) & 3) == 0;
+    if (whole) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t by[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int o = c * 16 + i * 4 + j;
+            by[3 * j + (2 - c)] = quant_u8(acc[o] + s_bias[o] + base[c]);
+          }
+        const size_t d = ((static_cast<size_t>(n) * a.dst_h + (a.dst_y0 + cy0 + i)) * a.dst_w + (a.dst_x0 + cx0)) * 3;
+        uint32_t* dw = reinterpret_cast<uint32_t*>(a.dst + d);
+#pragma unroll
+        for (int w4 = 0; w4 < 3; ++w4)
+          dw[w4] = by[4 * w4] | (by[4 * w4 + 1] << 8) | (by[4 * w4 + 2] << 16) | (by[4 * w4 + 3] << 24);
+      }
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int cy = y * 4 + i - a.crop_y0;
@@ -434,10 +473,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
   using Cfg = ConvCfg<COUT>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sW = smem;                                   // NWBUF x WCHUNK_BYTES
-  uint8_t* sA = smem + Cfg::NWBUF * Cfg::WCHUNK_BYTES;   // NSTAGES x A_STAGE_BYTES
+  const bool wres = args.w_resident != 0;                 // weights loaded once, one buffer (single-chunk convs)
+  const int NST = wres ? Cfg::NSTAGES_RES : Cfg::NSTAGES;  // activation stages in the ring
+  uint8_t* sW = smem;                                     // NWBUF (resident: 1) x WCHUNK_BYTES
+  uint8_t* sA = smem + (wres ? 1 : Cfg::NWBUF) * Cfg::WCHUNK_BYTES;   // NST x A_STAGE_BYTES
 
-  __shared__ uint64_t bar_full[Cfg::NSTAGES], bar_empty[Cfg::NSTAGES];
+  __shared__ uint64_t bar_full[Cfg::MAXSTAGES], bar_empty[Cfg::MAXSTAGES];
   __shared__ uint64_t bar_wfull[Cfg::NWBUF], bar_wempty[Cfg::NWBUF];
   __shared__ uint64_t bar_rfull[Cfg::MAXTH], bar_rempty[Cfg::MAXTH];
   __shared__ uint32_t s_tmem_base;
@@ -453,7 +494,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
     s_prelu[threadIdx.x] = (EPI == EPI_PRELU_BF16) ? args.prelu[threadIdx.x] : 0.f;
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < Cfg::NSTAGES; ++i) {
+    for (int i = 0; i < Cfg::MAXSTAGES; ++i) {
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
     }
@@ -484,6 +525,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0, phase = 0, wb = 0, wphase = 0;
+    bool wload = true;   // resident weights: only the first (tile, chunk) loads them
     for (int t = blockIdx.x; t < args.ntiles; t += gridDim.x) {
       const int n = t / tiles_per_img;
       const int r = t - n * tiles_per_img;
@@ -492,8 +534,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
       const int x0 = tx * 128 - 1;
       const int y0 = ty * TH;
       for (int c = 0; c < args.nchunks; ++c) {
-        mbar_wait(&bar_wempty[wb], wphase ^ 1);
-        if (elect_one_sync()) {
+        if (!wres) mbar_wait(&bar_wempty[wb], wphase ^ 1);
+        if (wload && elect_one_sync()) {
           mbar_arrive_expect_tx(&bar_wfull[wb], Cfg::WCHUNK_BYTES);
           const uint8_t* wsrc = args.wpack + static_cast<size_t>(c) * Cfg::WCHUNK_BYTES;
 #pragma unroll
@@ -502,9 +544,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
                          wsrc + d * Cfg::WTILE_BYTES, Cfg::WTILE_BYTES);
         }
         __syncwarp();
+        if (wres) wload = false;
         for (int y = -1; y <= TH; ++y) {
           mbar_wait(&bar_empty[stage], phase ^ 1);
-          if (elect_one_sync()) {
+          if (args.abl & 4) {
+            if (elect_one_sync()) mbar_arrive(&bar_full[stage]);
+          } else if (elect_one_sync()) {
             mbar_arrive_expect_tx(&bar_full[stage], args.in_up2 ? 132 * 128 : Cfg::A_BOX_BYTES);
             if (args.in_up2)   // rows y0+y = -1 and >= H map to source rows -1 and >= H/2: zero-filled
               tma_load_5d(&amap, &bar_full[stage], sA + stage * Cfg::A_STAGE_BYTES, c * 64, 0, (x0 + 1) / 2 - 1,
@@ -515,12 +560,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
               tma_load_4d(&amap, &bar_full[stage], sA + stage * Cfg::A_STAGE_BYTES, c * 64, x0, y0 + y, n);
           }
           __syncwarp();
-          if (++stage == Cfg::NSTAGES) {
+          if (++stage == NST) {
             stage = 0;
             phase ^= 1;
           }
         }
-        if (++wb == Cfg::NWBUF) {
+        if (!wres && ++wb == Cfg::NWBUF) {
           wb = 0;
           wphase ^= 1;
         }
@@ -542,7 +587,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
         const int ks = (c == args.nchunks - 1) ? args.last_ksteps : 4;
         const bool first_chunk = (c == 0);
         const bool last_chunk = (c == args.nchunks - 1);
-        mbar_wait(&bar_wfull[wb], wphase);
+        if (!wres || tile_iter == 0) mbar_wait(&bar_wfull[wb], wphase);   // resident: loaded once, never released
         const uint64_t bdesc_w = bdesc0 + static_cast<uint64_t>((wb * Cfg::WCHUNK_BYTES) >> 4);
         if (args.sub) {
           // sub-pixel phase: vertical blocks [vlo, vhi] and dx tiles [dlo, dhi] only (the other weights are zero and
@@ -583,10 +628,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
               umma_commit(&bar_empty[stage]);
               const int R = y - 1 + vlo;                                   // the row this input row completes
               if (last_chunk && R >= 0 && R < TH) umma_commit(&bar_rfull[R]);
-              if (y == TH) umma_commit(&bar_wempty[wb]);
+              if (y == TH && !wres) umma_commit(&bar_wempty[wb]);
             }
             __syncwarp();
-            if (++stage == Cfg::NSTAGES) {
+            if (++stage == NST) {
               stage = 0;
               phase ^= 1;
             }
@@ -607,14 +652,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
           if (elect_one_sync()) {
             // first K16 step of the stage (may start a new accumulator row), then 11 (or 5) plain steps;
             // two straight-line variants so no per-MMA predicates are needed
-            if (new_row) {
+            if (args.abl & 2) {
+            } else if (new_row) {
               if (nblk > 1) umma_bf16(dcol, ad0, bd0, nblk == 3 ? idesc2 : idesc1, 1);
               umma_bf16(dcol + (nblk - 1) * COUT, ad0, bd0 + static_cast<uint64_t>(((nblk - 1) * COUT * 128) >> 4),
                         idesc1, 0);
             } else {
               umma_bf16(dcol, ad0, bd0, idesc_n, 1);
             }
-            if (ks == 4) {
+            if (args.abl & 2) {
+            } else if (ks == 4) {
 #pragma unroll
               for (int i = 1; i < 12; ++i) {
                 const int dx = i >> 2, k = i & 3;
@@ -631,16 +678,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
             }
             umma_commit(&bar_empty[stage]);                             // stage reusable once these MMAs retire
             if (last_chunk && y >= 1) umma_commit(&bar_rfull[y - 1]);   // output row y-1 is complete
-            if (y == TH) umma_commit(&bar_wempty[wb]);                  // weight buffer reusable
+            if (y == TH && !wres) umma_commit(&bar_wempty[wb]);         // weight buffer reusable
           }
           __syncwarp();
-          if (++stage == Cfg::NSTAGES) {
+          if (++stage == NST) {
             stage = 0;
             phase ^= 1;
           }
         }
         }
-        if (++wb == Cfg::NWBUF) {
+        if (!wres && ++wb == Cfg::NWBUF) {
           wb = 0;
           wphase ^= 1;
         }
@@ -682,7 +729,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_rempty[Y]);
         const int y = y0 + Y;
-        if (y < args.H && x < args.W) epilogue_pixel<COUT, EPI>(args, s_bias, s_prelu, acc, n, y, x);
+        if (y < args.H && x < args.W && !(args.abl & 1)) epilogue_pixel<COUT, EPI>(args, s_bias, s_prelu, acc, n, y, x);
       }
     }
   }

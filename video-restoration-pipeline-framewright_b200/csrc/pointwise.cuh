@@ -283,111 +283,102 @@ __device__ __forceinline__ float norm_sample(float x, float d, float rcp) {
   return __fmaf_rn(r, rcp, q0);
 }
 
-// Two pixels per thread (lane l of a warp owns pixels base + l and base + 32 + l), 16 output channels per pass: every
-// uniform weight pair feeds two FFMA2s, and 4 x 27 x 8 x 2 = 1728 FFMA2 + 432 LDCU.128 per thread replace the
-// 2 x (864 + 661) of the one-pixel form.
-#ifndef B200SR_FIRST_MINBLOCKS
-#define B200SR_FIRST_MINBLOCKS 5     // 5 blocks / SM (<= 102 registers): 0.62 ms against 0.715 at 4 (4 x 720p, same box)
-#endif
-__global__ void __launch_bounds__(128, B200SR_FIRST_MINBLOCKS) first_conv3_const_kernel(const FirstArgs a, const __grid_constant__ FirstWeights3 cw) {
-  const int xb = blockIdx.x * 256 + (threadIdx.x >> 5) * 64 + (threadIdx.x & 31);
+// One pixel per thread, both 32-channel halves fully unrolled: every FFMA2 (two IEEE fma.rn per instruction -- same
+// bits as scalar fmaf) takes its weight pair from a uniform register (LDCU.128), the input value is broadcast; 864
+// FFMA2 + 661 LDCU per pixel.  (A two-pixels-per-thread form with the channel loop rolled -- indexed LDC.64 weight
+// loads, register spills -- measured 0.62 ms for 4 x 720p but 4.8-7.2 ms for an SRVGG batch of 64 x 640x480; with the
+// division-free normalisation this form takes 0.49 ms and 2.5 ms)
+__global__ void __launch_bounds__(128, 5) first_conv3_const_kernel(const FirstArgs a, const __grid_constant__ FirstWeights3 cw) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int n = blockIdx.z;
-  if (xb >= a.W) return;
+  if (x >= a.W) return;
   const size_t img = static_cast<size_t>(n) * a.Hs * a.Ws * 3;
   const float d = a.src16 ? 65535.0f : 255.0f;
   const float rcp = a.src16 ? (1.0f / 65535.0f) : (1.0f / 255.0f);
-  float in[2][27];
+  float in[27];
 #pragma unroll
-  for (int p = 0; p < 2; ++p) {
-    const int x = xb + 32 * p;
+  for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yy = y + ky - 1, xx = x + kx - 1;
+      const bool ok = yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;   // conv zero padding outside the region
+      const int sy = reflect_src(a.oy + (ok ? yy : 0), a.Hs, a.H1);
+      const int sx = reflect_src(a.ox + (ok ? xx : 0), a.Ws, a.W1);
+      const size_t p = img + (static_cast<size_t>(sy) * a.Ws + sx) * 3;
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int yy = y + ky - 1, xx = x + kx - 1;
-        const bool ok = yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;   // conv zero padding outside the region
-        const int sy = reflect_src(a.oy + (ok ? yy : 0), a.Hs, a.H1);
-        const int sx = reflect_src(a.ox + (ok ? xx : 0), a.Ws, a.W1);
-        const size_t q = img + (static_cast<size_t>(sy) * a.Ws + sx) * 3;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {   // BGR -> RGB, img / max_range as upstream's pre_process
-          const float v = a.src16 ? static_cast<float>(__ldg(reinterpret_cast<const uint16_t*>(a.src) + q + 2 - c))
-                                  : static_cast<float>(__ldg(a.src + q + 2 - c));
-          in[p][(ky * 3 + kx) * 3 + c] = ok ? norm_sample(v, d, rcp) : 0.f;
-        }
-      }
-  }
-#pragma unroll 1                             // (rolled: the body is 432 FFMA2 long; unrolled x4 it thrashes the instruction cache)
-  for (int qd = 0; qd < 4; ++qd) {          // channels [16 qd, 16 qd + 16)
-    // packed fp32 FMAs (FFMA2: two IEEE fma.rn per instruction -- same bits as scalar fmaf): accumulator pairs of
-    // adjacent channels, the input value broadcast, the weight pair from a uniform register
-    float2 acc2[2][8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-      acc2[0][c] = acc2[1][c] = make_float2(cw.b[qd * 16 + 2 * c], cw.b[qd * 16 + 2 * c + 1]);
-#pragma unroll
-    for (int t = 0; t < 27; ++t) {
-      const float2 v0 = make_float2(in[0][t], in[0][t]), v1 = make_float2(in[1][t], in[1][t]);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float2 w2 = make_float2(cw.w[t][qd * 16 + 2 * c], cw.w[t][qd * 16 + 2 * c + 1]);
-        acc2[0][c] = __ffma2_rn(v0, w2, acc2[0][c]);
-        acc2[1][c] = __ffma2_rn(v1, w2, acc2[1][c]);
+      for (int c = 0; c < 3; ++c) {   // BGR -> RGB, img / max_range as upstream's pre_process
+        const float v = a.src16 ? static_cast<float>(__ldg(reinterpret_cast<const uint16_t*>(a.src) + p + 2 - c))
+                                : static_cast<float>(__ldg(a.src + p + 2 - c));
+        in[(ky * 3 + kx) * 3 + c] = ok ? norm_sample(v, d, rcp) : 0.f;
       }
     }
+  const size_t pix = (static_cast<size_t>(n) * a.H + y) * a.W + x;
+  const size_t loff = a.lo ? lo_off(n, y, x, a.H, a.W) : 0;
+  float* f0 = a.f0 ? a.f0 + trunk_off(n, y, x, a.H, a.W) : nullptr;
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      const int x = xb + 32 * p;
-      if (x >= a.W) continue;
-      float acc[16];
+  for (int half = 0; half < 2; ++half) {
+    float2 acc2[16];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        acc[2 * c] = acc2[p][c].x;
-        acc[2 * c + 1] = acc2[p][c].y;
-      }
-      if (cw.has_prelu) {
+    for (int c = 0; c < 16; ++c) acc2[c] = make_float2(cw.b[half * 32 + 2 * c], cw.b[half * 32 + 2 * c + 1]);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc[c] = acc[c] > 0.f ? acc[c] : acc[c] * cw.p[qd * 16 + c];
-      }
-      const size_t pix = (static_cast<size_t>(n) * a.H + y) * a.W + x;
-      __nv_bfloat16* o = a.out + pix * a.out_pitch + qd * 16;
-      uint32_t pk[8];
-      if (a.lo) {   // residual-stream pair: bf16 hi + e5m2 lo of the rounding residual (store_trunk_pair's split)
+    for (int t = 0; t < 27; ++t) {
+      const float2 vv = make_float2(in[t], in[t]);
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        acc2[c] = __ffma2_rn(vv, make_float2(cw.w[t][half * 32 + 2 * c], cw.w[t][half * 32 + 2 * c + 1]), acc2[c]);
+    }
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      acc[2 * c] = acc2[c].x;
+      acc[2 * c + 1] = acc2[c].y;
+    }
+    if (cw.has_prelu) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] = acc[c] > 0.f ? acc[c] : acc[c] * cw.p[half * 32 + c];
+    }
+    __nv_bfloat16* o = a.out + pix * a.out_pitch + half * 32;
+    if (a.lo) {   // residual-stream pair: bf16 hi + e5m2 lo of the rounding residual (store_trunk_pair's split)
+      uint32_t l[8];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t p[8];
         float res[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          pk[i] = pack_bf16x2(acc[2 * i], acc[2 * i + 1]);
-          res[2 * i] = acc[2 * i] - bf16lo_f32(pk[i]);
-          res[2 * i + 1] = acc[2 * i + 1] - bf16hi_f32(pk[i]);
+          const float v0 = acc[g * 16 + 2 * i], v1 = acc[g * 16 + 2 * i + 1];
+          p[i] = pack_bf16x2(v0, v1);
+          res[2 * i] = v0 - bf16lo_f32(p[i]);
+          res[2 * i + 1] = v1 - bf16hi_f32(p[i]);
         }
-        st_global_256(o, pk);
-        uint4 l;
-        l.x = f32x4_e5m2(res[0], res[1], res[2], res[3]);
-        l.y = f32x4_e5m2(res[4], res[5], res[6], res[7]);
-        l.z = f32x4_e5m2(res[8], res[9], res[10], res[11]);
-        l.w = f32x4_e5m2(res[12], res[13], res[14], res[15]);
-        *reinterpret_cast<uint4*>(a.lo + lo_off(n, y, x, a.H, a.W) + (qd >> 1) * LO_GSTRIDE + (qd & 1) * 16) = l;
-      } else {
+        st_global_256(o + g * 16, p);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) l[g * 4 + i] = f32x4_e5m2(res[4 * i], res[4 * i + 1], res[4 * i + 2], res[4 * i + 3]);
+      }
+      st_global_256(a.lo + loff + half * LO_GSTRIDE, l);
+    } else {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t p[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          pk[i] = a.out_fp16 ? pack_f16x2(acc[2 * i], acc[2 * i + 1]) : pack_bf16x2(acc[2 * i], acc[2 * i + 1]);
-        st_global_256(o, pk);
+          p[i] = a.out_fp16 ? pack_f16x2(acc[g * 16 + 2 * i], acc[g * 16 + 2 * i + 1])
+                            : pack_bf16x2(acc[g * 16 + 2 * i], acc[g * 16 + 2 * i + 1]);
+        st_global_256(o + g * 16, p);
       }
-      if (a.f0) {
-        float* f0 = a.f0 + trunk_off(n, y, x, a.H, a.W) + static_cast<size_t>(qd * 2) * TRUNK_GSTRIDE;
+    }
+    if (f0) {
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          uint32_t q[8];
+      for (int g = 0; g < 4; ++g) {
+        uint32_t q[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) q[i] = __float_as_uint(acc[g * 8 + i]);
-          st_global_256(f0 + g * TRUNK_GSTRIDE, q);
-        }
+        for (int i = 0; i < 8; ++i) q[i] = __float_as_uint(acc[g * 8 + i]);
+        st_global_256(f0 + static_cast<size_t>(half * 4 + g) * TRUNK_GSTRIDE, q);
       }
-      if (a.inrgb && qd == 0)   // centre tap
-        *reinterpret_cast<float4*>(a.inrgb + pix * 4) = make_float4(in[p][12], in[p][13], in[p][14], 0.f);
     }
   }
+  if (a.inrgb) *reinterpret_cast<float4*>(a.inrgb + pix * 4) = make_float4(in[12], in[13], in[14], 0.f);   // centre tap
 }
 
 // out[n][Y][X][:] = in[n][Y/2][X/2][:], 64 bf16 channels (F.interpolate(scale_factor=2, mode='nearest')).
