@@ -109,7 +109,12 @@ int b200sr_last_launch_count(const b200sr_engine* e);
 /* Debug / measurement hooks (not part of the reference surface).
  * Options: "fused_rdb" (1: one persistent kernel per residual dense block; 0: five per-conv launches, same bytes),
  * "fold_up" (1: conv_up1/up2 read the nearest-2x upsampling through the duplicated-pixel TMA view; 0: materialise it),
- * "w_resident" (1: convs with Cin <= 64 load their weights once per CTA and use the space for more activation stages),
+ * "trunk_lo" (where the residual stream's e5m2 lo part is used -- 0: in the RRDB-level skip only, 1: also in the first
+ * RDB's residual add, 2: the pair after every RDB),
+ * "pair" (1: single-chunk convs run through conv3x3_sc_kernel -- resident weights, row-pair stages; 0: the per-row
+ * conv3x3_tc_kernel, identical bytes), "last9" (1: conv_last with the kx taps stacked on N; 0: per-tap form, within 1 LSB),
+ * "w_resident" (per-row kernel only: convs with Cin <= 64 keep their weights resident), "abl" (timing ablations of the
+ * per-conv kernels -- 1 no epilogue stores, 2 no MMAs, 4 no TMA loads; results are wrong when set),
  * "profile" (1: CUDA events around every launch, read with b200sr_get_profile), "force_th", "max_ctas",
  * "lanes" (host-buffer lanes, default 2), "host_chunk" (frames per lane job, 0 = auto), "ws_limit_mb" (tests: refuse
  * larger workspaces with B200SR_ERR_OOM),

@@ -19,19 +19,23 @@ def _q(t: torch.Tensor, dtype) -> torch.Tensor:
 
 def emulate_rrdb(sd: Dict[str, torch.Tensor], img_bgr_u8: np.ndarray, scale: int = 4, num_block: int = 23,
                  act_dtype=torch.bfloat16, w_dtype=torch.bfloat16, trunk_copy_dtype="same", tail_dtype="same",
-                 first_dtype="same", tail_w_dtype="same", trunk_mode="hilo") -> np.ndarray:
+                 first_dtype="same", tail_w_dtype="same", trunk_mode="hybrid") -> np.ndarray:
     trunk_copy_dtype = act_dtype if trunk_copy_dtype == "same" else trunk_copy_dtype
     tail_dtype = act_dtype if tail_dtype == "same" else tail_dtype
     first_dtype = act_dtype if first_dtype == "same" else first_dtype
     tail_w_dtype = w_dtype if tail_w_dtype == "same" else tail_w_dtype
 
-    def tq(v):
-        """Residual-stream storage: "hilo" = bf16 hi (the conv-input copy) + e5m2 lo (the engine, conv3x3_tc.cuh
-        TrunkLo), "f32", or "bf16" alone."""
+    def tq(v, rrdb_end=True):
+        """Residual-stream storage: "hybrid" (the engine, conv3x3_tc.cuh TrunkLo) = bf16 hi (the conv-input copy) +
+        e5m2 lo at RRDB boundaries, hi alone inside an RRDB, and the lo part used by the RRDB-level skip only (option
+        trunk_lo = 0); "hybrid1" = lo also in the first RDB's residual add (trunk_lo = 1); "hilo" = the pair after
+        every RDB (trunk_lo = 2); "f32"; or "bf16" alone."""
         if trunk_mode == "f32":
             return v
         hi = _q(v, torch.bfloat16)
-        return hi if trunk_mode == "bf16" else hi + (v - hi).to(torch.float8_e5m2).float()
+        if trunk_mode == "bf16" or (trunk_mode in ("hybrid", "hybrid1") and not rrdb_end):
+            return hi
+        return hi + (v - hi).to(torch.float8_e5m2).float()
 
     def conv(x, name, wq=True, wd="trunk"):
         w = sd[name + ".weight"].float()
@@ -56,9 +60,9 @@ def emulate_rrdb(sd: Dict[str, torch.Tensor], img_bgr_u8: np.ndarray, scale: int
                 xk = F.leaky_relu(conv(cat, p + f"conv{k}"), 0.2)
                 cat = torch.cat((cat, _q(xk, act_dtype)), 1)
             x5 = conv(cat, p + "conv5")
-            v = x5 * 0.2 + trunk
+            v = x5 * 0.2 + (_q(trunk, torch.bfloat16) if (trunk_mode == "hybrid" and r == 1) else trunk)
             # RRDB-level skip fused in the rdb3 epilogue: x <- ((acc+b)*0.2 + x)*0.2 + x0
-            trunk = tq(v * 0.2 + x0 if r == 3 else v)
+            trunk = tq(v * 0.2 + x0) if r == 3 else tq(v, rrdb_end=False)
     body = conv(_q(trunk, trunk_copy_dtype), "conv_body")
     feat = _q(feat + body, tail_dtype)
     feat = _q(F.leaky_relu(conv(F.interpolate(feat, scale_factor=2, mode="nearest"), "conv_up1", wd="tail"), 0.2), tail_dtype)

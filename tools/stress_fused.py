@@ -5,8 +5,9 @@
 
 Every iteration draws a random shape (ragged heights / widths around the strip, flag-block and column-tile
 boundaries), a random batch and a random `max_ctas` between 1 and 148 (fewer resident CTAs than work items, down to
-ONE CTA that must run the whole dependency graph by itself in claim order), runs the per-conv schedule as the
-reference and the fused schedule twice, and compares bytes.  Run it with B200SR_LIB=libb200sr_debug.so to execute
+ONE CTA that must run the whole dependency graph by itself in claim order), runs the per-conv schedule (and the
+per-row conv kernel) as the reference, the fused schedule + the row-pair single-chunk kernel twice, and compares bytes;
+the stacked-kx conv_last (another fp32 summation order) must stay within 1 LSB.  Run it with B200SR_LIB=libb200sr_debug.so to execute
 the build with bounds traps on every flag index, item field and TMA coordinate (`-DB200SR_DEBUG`).
 `--big` adds the full-size shapes (4 x 720p, 1080p x2, the 720p tile regions)."""
 import argparse
@@ -44,12 +45,21 @@ def main() -> int:
         w = int(rng.choice(wedges)) if rng.random() < 0.5 else int(rng.integers(8, 700))
         ctas = int(rng.choice([1, 2, 3, 5, 8, 17, 37, 74, 147, 148])) if rng.random() < 0.7 else 0
         x = torch.from_numpy(rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)).cuda()
+        # reference: five per-conv launches per RDB and the per-row conv kernel everywhere (pair = 0); under test: the
+        # fused RDB kernel + the row-pair single-chunk kernel (bit-identical), then the stacked-kx conv_last on top
+        # (different fp32 summation order: within 1 LSB)
         eng.set_option("max_ctas", 0)
         eng.set_option("fused_rdb", 0)
+        eng.set_option("pair", 0)
+        eng.set_option("last9", 0)
         ref = eng.upscale_device(x).clone()
         eng.set_option("fused_rdb", 1)
+        eng.set_option("pair", 1)
         eng.set_option("max_ctas", ctas)
         ok = all(torch.equal(eng.upscale_device(x), ref) for _ in range(2))
+        eng.set_option("last9", 1)
+        d9 = (eng.upscale_device(x).to(torch.int16) - ref.to(torch.int16)).abs().max().item()
+        ok = ok and d9 <= 1
         torch.cuda.synchronize()
         bad += 0 if ok else 1
         print(f"[{it:3d}] {n}x{h}x{w} max_ctas={ctas or 148}: {'ok' if ok else 'MISMATCH'}", flush=True)

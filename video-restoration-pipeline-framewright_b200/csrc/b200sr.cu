@@ -122,6 +122,9 @@ struct b200sr_engine {
   int opt_fused_rdb = 1;    // run each RDB as one persistent kernel (L2-resident intermediates)
   int opt_first_v1 = 0;     // input stage: 0 = constant-bank kernel (3 ch) / tiled kernel (12 ch); 1 = round-1 per-pixel
                             // kernel; 2 = tiled kernel for 3 ch too (all bit-identical; tests / A-B timing)
+  int opt_trunk_lo = 0;     // where the residual stream's e5m2 lo part is used: 0 = in the RRDB-level skip only (written
+                            // at every RRDB end, read at the next one); 1 = also in the first RDB's own residual add;
+                            // 2 = the pair after EVERY RDB (rounds 1-2a)
   int opt_pair = 1;         // single-chunk convs through conv3x3_sc_kernel (resident weights, row-pair stages)
   int opt_last9 = 1;        // conv_last with the kx taps stacked on N (needs opt_pair)
   int opt_abl = 0;          // dev: timing ablations of the per-conv kernel (ConvArgs::abl); results are wrong when set
@@ -882,8 +885,9 @@ int run_region(b200sr_engine* e, Lane* lane, const Region& R, cudaStream_t st) {
         __nv_bfloat16* Din = D[r];
         __nv_bfloat16* Dout = D[(r + 1) % 3];
         TrunkIO tio;
-        tio.lo_in = r == 0 ? loB : loA;
-        tio.lo_out = r == 2 ? loB : loA;
+        // the pair lives at the RRDB boundaries (loB); inside an RRDB the stream is hi alone unless trunk_lo = 2
+        tio.lo_in = r == 0 ? (e->opt_trunk_lo >= 1 ? loB : nullptr) : (e->opt_trunk_lo >= 2 ? loA : nullptr);
+        tio.lo_out = r == 2 ? loB : (e->opt_trunk_lo >= 2 ? loA : nullptr);
         tio.xb_hi = D[0];
         tio.xb_lo = loB;
         if (e->opt_fused_rdb) {
@@ -1524,6 +1528,10 @@ int b200sr_set_option(b200sr_engine* e, const char* key, int value) {
   }
   if (!strcmp(key, "fold_up")) {
     e->opt_fold_up = value;
+    return B200SR_OK;
+  }
+  if (!strcmp(key, "trunk_lo")) {
+    e->opt_trunk_lo = value;
     return B200SR_OK;
   }
   if (!strcmp(key, "pair")) {

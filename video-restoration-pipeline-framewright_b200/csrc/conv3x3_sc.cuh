@@ -114,7 +114,9 @@ conv3x3_sc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
       const int y0 = ty * TH;
       for (int p = 0; p < npairs_in; ++p) {
         mbar_wait(&bar_empty[ps], phase ^ 1);   // rows 2p - 1 and 2p; the second exists while 2p <= TH
-        if (elect_one_sync()) {
+        if (args.abl & 4) {   // (timing ablation: no activation loads)
+          if (elect_one_sync()) mbar_arrive(&bar_full[ps]);
+        } else if (elect_one_sync()) {
           mbar_arrive_expect_tx(&bar_full[ps], (2 * p <= TH ? 2u : 1u) * box_bytes);
           for (int j = 0; j < 2; ++j) {
             const int y = 2 * p - 1 + j;
@@ -155,7 +157,7 @@ conv3x3_sc_kernel(const __grid_constant__ CUtensorMap amap, const ConvArgs args)
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             const int y = 2 * p - 1 + j;
-            if (y <= TH) {
+            if (y <= TH && !(args.abl & 2)) {   // (abl & 2: timing ablation, no MMAs)
               const int blk_lo = (y < 1) ? (1 - y) : 0;        // output row y-1+blk must be >= 0
               const int blk_hi = (TH - y < 2) ? (TH - y) : 2;  // and < TH
               const int nblk = blk_hi - blk_lo + 1;

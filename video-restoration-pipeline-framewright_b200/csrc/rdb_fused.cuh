@@ -140,6 +140,12 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
   } while (0)
 #endif
 
+// EXPERIMENT: dense-block intermediates (planes 1, 2) addressed modulo a ring of this many rows, so that dead rows are
+// overwritten while still in L2 instead of being written back to DRAM (0 = off: full-frame planes)
+#ifndef B200SR_RDB_RING
+#define B200SR_RDB_RING 0
+#endif
+constexpr int RDB_RING = B200SR_RDB_RING;
 #ifndef B200SR_RDB_QD
 #define B200SR_RDB_QD 2
 #endif
@@ -353,7 +359,8 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
           if (lane == 0) {   // (the lane that executed the fences above)
             RDB_ASSERT(r >= -1 && r <= L.H && x0 >= -1 && x0 < L.W && c * L.N + item.n < 3 * L.N, "TMA coordinate", r, x0);
             mbar_arrive_expect_tx(&bar_full[stage], 130 * 128);
-            tma_load_4d_hint(&amap, &bar_full[stage], sA + stage * RDB_A_STAGE_BYTES, 0, x0, r, c * L.N + item.n, pol);
+            const int rr = (RDB_RING > 0 && c > 0 && r >= 0 && r < L.H) ? r % RDB_RING : r;
+            tma_load_4d_hint(&amap, &bar_full[stage], sA + stage * RDB_A_STAGE_BYTES, 0, x0, rr, c * L.N + item.n, pol);
           }
           __syncwarp();
           if (++stage == RDB_NSTAGES) {
@@ -625,7 +632,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
           const size_t o = lo_off(n, item.y0 + Y, item.tx * 128 + q * 32, L.H, L.W) + (lane & 7) * 128 +
                            static_cast<size_t>((lane >> 3) & 1) * LO_GSTRIDE;
           if (lane < 16) {
-            prefetch_l2(L.lo_in + o);
+            if (L.lo_in) prefetch_l2(L.lo_in + o);
             if (args.rrdb_end) prefetch_l2(L.xb_lo + o);
           }
         }
@@ -642,7 +649,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
               if (args.rrdb_end)
                 load_trunk_pair(L.xb_hi + pix * L.out_pitch, L.xb_lo + loff, ph, pl);
               else
-                load_trunk_pair(L.hi_in + pix * L.out_pitch, L.lo_in + loff, ph, pl);
+                load_trunk_pair(L.hi_in + pix * L.out_pitch, L.lo_in ? L.lo_in + loff : nullptr, ph, pl);
             }
             RDB_TIMED(0, mbar_wait(&bar_rfull[sl], (rfull_par >> sl) & 1u));
             if (q == 2 && lane == 0) RDB_STAMP2(it, Y, 1);
@@ -659,7 +666,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
               if (x < L.W && !(B200SR_ABL_NOEPI & 2)) {
                 if (args.rrdb_end) {
                   uint32_t xh[4][8], xl[2][8];
-                  load_trunk_pair(L.hi_in + pix * L.out_pitch, L.lo_in + loff, xh, xl);
+                  load_trunk_pair(L.hi_in + pix * L.out_pitch, L.lo_in ? L.lo_in + loff : nullptr, xh, xl);
                   trunk_pixel<true>(L, s_bias[4], acc, xh, xl, ph, pl, n, item.y0 + Y, x);
                 } else {
                   trunk_pixel<false>(L, s_bias[4], acc, ph, pl, ph, pl, n, item.y0 + Y, x);
@@ -684,7 +691,8 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             if (lane == 0) mbar_arrive(&bar_rempty[Y]);
             RDB_TIMED(5, {
               if (x < L.W && !(B200SR_ABL_NOEPI & 1))
-                epilogue_pixel<32, EPI_ACT_BF16>(L, s_bias[item.k], s_bias[item.k], acc, n, item.y0 + Y, x);
+                epilogue_pixel<32, EPI_ACT_BF16>(L, s_bias[item.k], s_bias[item.k], acc, n,
+                                                 RDB_RING > 0 ? (item.y0 + Y) % RDB_RING : item.y0 + Y, x);
             });
             RDB_COUNT(6, 1);
             if (q == 2 && lane == 0) RDB_STAMP2(it, Y, 2);
