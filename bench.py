@@ -383,7 +383,7 @@ def run_b200(args):
     # DRAM traffic of the dominant kernel, per launch, from the committed `ncu --set full` capture of this command's
     # kernel at the same frames-per-launch (profiles/r0x_rdb_fused_traffic.json; null if the batch differs)
     traffic = None
-    for tname in ("r02_rdb_fused_traffic.json", "r01_rdb_fused_traffic.json"):
+    for tname in ("r02b_rdb_fused_traffic.json", "r02_rdb_fused_traffic.json", "r01_rdb_fused_traffic.json"):
         tpath = os.path.join(ROOT, "profiles", tname)
         if dom == "rdb_fused" and os.path.exists(tpath):
             with open(tpath) as f:
@@ -423,7 +423,7 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "dtype_detail": "bf16 RRDB trunk (residual stream bf16 hi + e5m2 lo), fp16 HR tail, fp32 accumulate",
+        "dtype": "bf16", "dtype_detail": "bf16 RRDB trunk (residual stream bf16, plus an e5m2 lo part at the RRDB boundaries), fp16 HR tail, fp32 accumulate",
         "data": "synthetic",
         "config": workload_config(B, world),
         "value_batch1": fps_batch1,

@@ -146,6 +146,11 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 #define B200SR_RDB_RING 0
 #endif
 constexpr int RDB_RING = B200SR_RDB_RING;
+// EXPERIMENT: conv5's epilogue discards (discard.global.L2: drop without write-back) the dense-block intermediates that
+// only its own item read -- rows y0+1 .. y0+rows-2, tile-interior pixels -- once all MMAs of the item have completed
+#ifndef B200SR_RDB_DISCARD
+#define B200SR_RDB_DISCARD 0
+#endif
 #ifndef B200SR_RDB_QD
 #define B200SR_RDB_QD 2
 #endif
@@ -678,6 +683,17 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
           }
           rfull_par ^= 1u << sl;   // every epilogue warp tracks every slot's phase
         }
+#if B200SR_RDB_DISCARD
+        // this group drained the item's last row: every MMA of the item (hence every TMA read it made) is complete
+        if (((item.rows - 1) % RDB_NGRP) == eg && m >= 1 && m <= 126 && x + 1 < L.W) {
+          const size_t plane = static_cast<size_t>(L.N) * L.H * L.W * 64;
+          for (int Y = 1; Y <= item.rows - 2; ++Y) {
+            const __nv_bfloat16* px = L.hi_in + ((static_cast<size_t>(n) * L.H + item.y0 + Y) * L.W + x) * 64;
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(px + plane) : "memory");
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(px + 2 * plane) : "memory");
+          }
+        }
+#endif
       } else {
         for (int Y = 0; Y < item.rows; ++Y) {
           if ((Y % RDB_NGRP) == eg) {
