@@ -111,6 +111,7 @@ int b200sr_last_launch_count(const b200sr_engine* e);
  * "fold_up" (1: conv_up1/up2 read the nearest-2x upsampling through the duplicated-pixel TMA view; 0: materialise it),
  * "trunk_lo" (where the residual stream's e5m2 lo part is used -- 0: in the RRDB-level skip only, 1: also in the first
  * RDB's residual add, 2: the pair after every RDB),
+ * "fuse_tail" (1: conv_hr + conv_last as one rolling kernel, the 4x tensor between them stays on chip; identical bytes),
  * "pair" (1: single-chunk convs run through conv3x3_sc_kernel -- resident weights, row-pair stages; 0: the per-row
  * conv3x3_tc_kernel, identical bytes), "last9" (1: conv_last with the kx taps stacked on N; 0: per-tap form, within 1 LSB),
  * "w_resident" (per-row kernel only: convs with Cin <= 64 keep their weights resident), "abl" (timing ablations of the
@@ -122,8 +123,8 @@ int b200sr_last_launch_count(const b200sr_engine* e);
 int b200sr_set_option(b200sr_engine* e, const char* key, int value);
 
 /* Per-kernel-class timing collected while option "profile" is 1 (CUDA events around every launch).
- * Arrays of length nclass >= 11, indexed: 0 conv<32,act> 1 conv<64,act> 2 conv<64,prelu> 3 conv<64,rdb5>
- * 4 conv<64,rdb5+rrdb> 5 conv<64,add> 6 conv<16,last_u8> 7 conv<48,srvgg_last> 8 first_conv 9 upsample2x 10 rdb_fused.
+ * Arrays of length nclass >= 12, indexed: 0 conv<32,act> 1 conv<64,act> 2 conv<64,prelu> 3 conv<64,rdb5>
+ * 4 conv<64,rdb5+rrdb> 5 conv<64,add> 6 conv<16,last_u8> 7 conv<48,srvgg_last> 8 first_conv 9 upsample2x 10 rdb_fused 11 hr_last_fused.
  * flops = algorithmic FLOPs (true channel counts).  Clears the collected records. */
 int b200sr_get_profile(b200sr_engine* e, int nclass, double* ms, double* flops, int* launches);
 

@@ -58,8 +58,11 @@ def main() -> int:
         eng.set_option("max_ctas", ctas)
         ok = all(torch.equal(eng.upscale_device(x), ref) for _ in range(2))
         eng.set_option("last9", 1)
-        d9 = (eng.upscale_device(x).to(torch.int16) - ref.to(torch.int16)).abs().max().item()
-        ok = ok and d9 <= 1
+        eng.set_option("fuse_tail", 0)
+        y9 = eng.upscale_device(x).clone()
+        d9 = (y9.to(torch.int16) - ref.to(torch.int16)).abs().max().item()
+        eng.set_option("fuse_tail", 1)                      # conv_hr + conv_last as one rolling kernel: same bytes
+        ok = ok and d9 <= 1 and torch.equal(eng.upscale_device(x), y9)
         torch.cuda.synchronize()
         bad += 0 if ok else 1
         print(f"[{it:3d}] {n}x{h}x{w} max_ctas={ctas or 148}: {'ok' if ok else 'MISMATCH'}", flush=True)

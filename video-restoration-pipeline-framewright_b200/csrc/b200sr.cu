@@ -21,6 +21,7 @@
 #include "../../include/b200sr.h"
 #include "conv3x3_tc.cuh"
 #include "conv3x3_sc.cuh"
+#include "hr_last_fused.cuh"
 #include "pointwise.cuh"
 #include "rdb_fused.cuh"
 #include "tmap.h"
@@ -125,6 +126,7 @@ struct b200sr_engine {
   int opt_trunk_lo = 0;     // where the residual stream's e5m2 lo part is used: 0 = in the RRDB-level skip only (written
                             // at every RRDB end, read at the next one); 1 = also in the first RDB's own residual add;
                             // 2 = the pair after EVERY RDB (rounds 1-2a)
+  int opt_fuse_tail = 1;    // conv_hr + conv_last as one kernel (hr_last_fused.cuh; needs opt_pair and opt_last9)
   int opt_pair = 1;         // single-chunk convs through conv3x3_sc_kernel (resident weights, row-pair stages)
   int opt_last9 = 1;        // conv_last with the kx taps stacked on N (needs opt_pair)
   int opt_abl = 0;          // dev: timing ablations of the per-conv kernel (ConvArgs::abl); results are wrong when set
@@ -148,7 +150,7 @@ struct b200sr_engine {
 
 enum ProfClass {
   PC_CONV32_ACT = 0, PC_CONV64_ACT, PC_CONV64_PRELU, PC_CONV64_RDB5, PC_CONV64_RDB5_RRDB, PC_CONV64_ADD,
-  PC_CONV16_LAST, PC_CONV48_SRVGG_LAST, PC_FIRST, PC_UPSAMPLE, PC_RDB_FUSED, PC_COUNT
+  PC_CONV16_LAST, PC_CONV48_SRVGG_LAST, PC_FIRST, PC_UPSAMPLE, PC_RDB_FUSED, PC_HR_LAST, PC_COUNT
 };
 
 namespace {
@@ -438,6 +440,62 @@ int launch_conv(b200sr_engine* e, Lane* lane, const Layer& l, int epi, const Con
     case 48 * 16 + EPI_SRVGG_LAST: return launch_conv_inst<48, EPI_SRVGG_LAST>(e, lane, amap, a, st, PC_CONV48_SRVGG_LAST, fl);
     default: return fail(e, B200SR_ERR_INVALID, "no kernel instance for this (Cout, epilogue)");
   }
+}
+
+// conv_hr + conv_last as one rolling kernel (hr_last_fused.cuh).  `in` = conv_up2's output [N][H][W][64] fp16.
+int launch_hr_last_fused(b200sr_engine* e, Lane* lane, const Layer& l_hr, const Layer& l_last, const void* in, int N, int H,
+                         int W, const ConvArgs& base, cudaStream_t st) {
+  CUtensorMap amap;
+  if (!tmap_encode_act(&amap, in, N, H, W, 64, 64, 130, 128)) return fail(e, B200SR_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  HrLastArgs a{};
+  a.N = N;
+  a.H = H;
+  a.W = W;
+  a.xtiles = (W + 125) / 126;
+  // strips per column tile: balance the waves (a unit costs its rows + 4 halo rows)
+  const int slots = e->opt_max_ctas > 0 ? e->opt_max_ctas : e->num_sms;
+  double best = 1e30;
+  int best_rows = (H + 1) / 2 * 2;
+  for (int S = 1; S <= std::max(1, H / 16); ++S) {
+    const int rows = ((H + S - 1) / S + 1) / 2 * 2;
+    const long units = static_cast<long>(N) * a.xtiles * ((H + rows - 1) / rows);
+    const double cost = static_cast<double>((units + slots - 1) / slots) * (rows + 4.0);
+    if (cost < best - 1e-9) {
+      best = cost;
+      best_rows = rows;
+    }
+  }
+  if (e->opt_force_th > 0) best_rows = std::max(2, (e->opt_force_th + 1) / 2 * 2);   // tests: ragged / tiny strips
+  a.strip_rows = best_rows;
+  a.strips = (H + best_rows - 1) / best_rows;
+  a.nunits = N * a.xtiles * a.strips;
+  a.w_hr = l_hr.d_wpack;
+  a.w_last = l_last.d_wlast9;
+  a.bias_hr = l_hr.d_bias;
+  a.bias_last = l_last.d_bias;
+  a.slope = 0.2f;
+  a.dst = base.dst;
+  a.dst16 = base.dst16;
+  a.dst_h = base.dst_h;
+  a.dst_w = base.dst_w;
+  a.crop_y0 = base.crop_y0;
+  a.crop_x0 = base.crop_x0;
+  a.crop_h = base.crop_h;
+  a.crop_w = base.crop_w;
+  a.dst_y0 = base.dst_y0;
+  a.dst_x0 = base.dst_x0;
+  const double px = static_cast<double>(N) * H * W;
+  ProfScope prof_scope(e, PC_HR_LAST, 2.0 * 9.0 * (64.0 * 64.0 + 64.0 * 3.0) * px, st);
+  static bool attr_done[16] = {};
+  if (!attr_done[e->device & 15]) {
+    CUDA_TRY(e, cudaFuncSetAttribute(hr_last_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES));
+    attr_done[e->device & 15] = true;
+  }
+  const int grid = std::min(a.nunits, slots);
+  hr_last_fused_kernel<<<grid, HL_NTHREADS, HL_SMEM_BYTES, st>>>(amap, a);
+  CUDA_TRY(e, cudaGetLastError());
+  lane->launches++;
+  return B200SR_OK;
 }
 
 // ---- workspace layout for one region of conv-domain size N x H x W ----
@@ -980,6 +1038,12 @@ int run_region(b200sr_engine* e, Lane* lane, const Region& R, cudaStream_t st) {
       }
       rc = conv_up(l_up2, U2, U3, U4, 2 * H, 2 * W);
       if (rc) return rc;
+      if (e->opt_fuse_tail && e->opt_pair && e->opt_last9 && l_last.d_wlast9 && B200SR_CTAS_PER_SM == 1) {
+        // conv_hr + lrelu + conv_last + clamp/round/quantise + crop in one kernel: the 4x tensor between them stays on chip
+        rc = launch_hr_last_fused(e, lane, l_hr, l_last, U4, n, 4 * H, 4 * W, tb, st);
+        if (rc) return rc;
+        continue;
+      }
       {  // conv_hr + lrelu
         ConvIO io{U4, 64, n, 4 * H, 4 * W};
         ConvArgs a = tb;
@@ -1532,6 +1596,10 @@ int b200sr_set_option(b200sr_engine* e, const char* key, int value) {
   }
   if (!strcmp(key, "trunk_lo")) {
     e->opt_trunk_lo = value;
+    return B200SR_OK;
+  }
+  if (!strcmp(key, "fuse_tail")) {
+    e->opt_fuse_tail = value;
     return B200SR_OK;
   }
   if (!strcmp(key, "pair")) {

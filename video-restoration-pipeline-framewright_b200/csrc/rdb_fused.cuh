@@ -168,13 +168,18 @@ constexpr int RDB_QD = B200SR_RDB_QD;
 #endif
 constexpr int RDB_CTAS = B200SR_RDB_CTAS;
 static_assert(RDB_CTAS == 1 || RDB_CTAS == 2, "B200SR_RDB_CTAS must be 1 or 2");
-constexpr int RDB_TMEM_COLS = 512 / RDB_CTAS;
+// EXPERIMENT: -DB200SR_RDB_TMEM_COLS=256 with one CTA per SM = items of 8 rows (conv5: 4): half the bytes per step of the
+// skewed schedule, i.e. half the L2 working window, for more halo rows and weight reloads per output row
+#ifndef B200SR_RDB_TMEM_COLS
+#define B200SR_RDB_TMEM_COLS (512 / B200SR_RDB_CTAS)
+#endif
+constexpr int RDB_TMEM_COLS = B200SR_RDB_TMEM_COLS;
 constexpr int RDB_TH4 = RDB_TMEM_COLS / 32;        // output rows of a conv1..4 item (one 32-column slot per row)
 constexpr int RDB_TH5 = RDB_TMEM_COLS / 64;        // output rows of a conv5 item
 constexpr int RDB_STRIP_ROWS = RDB_TH4;            // rows per strip of the skewed schedule
 constexpr int RDB_SHIFT_ROWS = RDB_TH4 / 2;        // conv k is shifted up by k * RDB_SHIFT_ROWS rows
 #ifndef B200SR_RDB_FLAG_SHIFT
-#define B200SR_RDB_FLAG_SHIFT (B200SR_RDB_CTAS == 1 ? 3 : 2)
+#define B200SR_RDB_FLAG_SHIFT (B200SR_RDB_TMEM_COLS == 512 ? 3 : 2)
 #endif
 constexpr int RDB_FLAG_SHIFT = B200SR_RDB_FLAG_SHIFT;   // completion counters per 2^shift output rows of a conv
 constexpr int RDB_FLAG_ROWS = 1 << RDB_FLAG_SHIFT;

@@ -202,7 +202,7 @@ class B200Engine:
         return out[0] if single else out
 
     PROFILE_CLASSES = ["conv32_act", "conv64_act", "conv64_prelu", "conv64_rdb5", "conv64_rdb5_rrdb", "conv64_add",
-                       "conv16_last_u8", "conv48_srvgg_last", "first_conv", "upsample2x", "rdb_fused"]
+                       "conv16_last_u8", "conv48_srvgg_last", "first_conv", "upsample2x", "rdb_fused", "hr_last_fused"]
 
     def get_profile(self) -> Dict[str, Dict[str, float]]:
         """Per-kernel-class {ms, flops, launches} collected since the last call (needs set_option('profile', 1))."""
