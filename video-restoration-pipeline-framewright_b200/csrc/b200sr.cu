@@ -20,8 +20,13 @@
 
 #include "../../include/b200sr.h"
 #include "conv3x3_tc.cuh"
+#if B200SR_CTAS_PER_SM == 1   // (the 2-CTAs-per-SM dev build of the per-row kernel has no room for these)
 #include "conv3x3_sc.cuh"
 #include "hr_last_fused.cuh"
+#define B200SR_HAVE_SC 1
+#else
+#define B200SR_HAVE_SC 0
+#endif
 #include "pointwise.cuh"
 #include "rdb_fused.cuh"
 #include "tmap.h"
@@ -321,6 +326,7 @@ std::vector<uint8_t> pack_weights_last9(const Layer& l) {
   return img;
 }
 
+#if B200SR_HAVE_SC
 template <int COUT, int EPI>
 int launch_sc_inst(b200sr_engine* e, Lane* lane, const CUtensorMap& amap, const ConvArgs& a, cudaStream_t st,
                    int pcls, double flops) {
@@ -338,6 +344,8 @@ int launch_sc_inst(b200sr_engine* e, Lane* lane, const CUtensorMap& amap, const 
   lane->launches++;
   return B200SR_OK;
 }
+
+#endif
 
 template <int COUT, int EPI>
 int launch_conv_inst(b200sr_engine* e, Lane* lane, const CUtensorMap& amap, const ConvArgs& a, cudaStream_t st,
@@ -410,9 +418,10 @@ int launch_conv(b200sr_engine* e, Lane* lane, const Layer& l, int epi, const Con
   // algorithmic FLOPs of this launch: true channel counts, every output pixel, 9 taps (a sub-pixel phase launch
   // produces N x H x W of the 4 N H W output pixels of the upsample + conv it implements, with 4 issued taps each)
   const double fl = 2.0 * 9.0 * l.cin * l.cout * static_cast<double>(io.N) * io.H * io.W;
+#if B200SR_HAVE_SC
   if (a.nchunks == 1 && !a.sub && e->opt_pair && l.cin == 64) {
     // product path of every single-chunk conv: resident weights, row-pair stages (conv3x3_sc.cuh)
-    if (epi == EPI_LAST_U8 && e->opt_last9 && l.d_wlast9 && B200SR_CTAS_PER_SM == 1) {
+    if (epi == EPI_LAST_U8 && e->opt_last9 && l.d_wlast9) {
       a.wpack = l.d_wlast9;
       a.TH = choose_th(e, 32, io.N, io.H, io.W, 126);
       a.xtiles = (io.W + 125) / 126;
@@ -429,6 +438,7 @@ int launch_conv(b200sr_engine* e, Lane* lane, const Layer& l, int epi, const Con
       default: break;   // (Cout = 32 single-chunk convs: RDB conv1 through the per-conv path, tests only)
     }
   }
+#endif
   switch (l.coutp * 16 + epi) {
     case 32 * 16 + EPI_ACT_BF16: return launch_conv_inst<32, EPI_ACT_BF16>(e, lane, amap, a, st, PC_CONV32_ACT, fl);
     case 64 * 16 + EPI_ACT_BF16: return launch_conv_inst<64, EPI_ACT_BF16>(e, lane, amap, a, st, PC_CONV64_ACT, fl);
@@ -442,6 +452,7 @@ int launch_conv(b200sr_engine* e, Lane* lane, const Layer& l, int epi, const Con
   }
 }
 
+#if B200SR_HAVE_SC
 // conv_hr + conv_last as one rolling kernel (hr_last_fused.cuh).  `in` = conv_up2's output [N][H][W][64] fp16.
 int launch_hr_last_fused(b200sr_engine* e, Lane* lane, const Layer& l_hr, const Layer& l_last, const void* in, int N, int H,
                          int W, const ConvArgs& base, cudaStream_t st) {
@@ -497,6 +508,7 @@ int launch_hr_last_fused(b200sr_engine* e, Lane* lane, const Layer& l_hr, const 
   lane->launches++;
   return B200SR_OK;
 }
+#endif
 
 // ---- workspace layout for one region of conv-domain size N x H x W ----
 struct Region {
@@ -1038,12 +1050,14 @@ int run_region(b200sr_engine* e, Lane* lane, const Region& R, cudaStream_t st) {
       }
       rc = conv_up(l_up2, U2, U3, U4, 2 * H, 2 * W);
       if (rc) return rc;
-      if (e->opt_fuse_tail && e->opt_pair && e->opt_last9 && l_last.d_wlast9 && B200SR_CTAS_PER_SM == 1) {
+#if B200SR_HAVE_SC
+      if (e->opt_fuse_tail && e->opt_pair && e->opt_last9 && l_last.d_wlast9) {
         // conv_hr + lrelu + conv_last + clamp/round/quantise + crop in one kernel: the 4x tensor between them stays on chip
         rc = launch_hr_last_fused(e, lane, l_hr, l_last, U4, n, 4 * H, 4 * W, tb, st);
         if (rc) return rc;
         continue;
       }
+#endif
       {  // conv_hr + lrelu
         ConvIO io{U4, 64, n, 4 * H, 4 * W};
         ConvArgs a = tb;
