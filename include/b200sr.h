@@ -111,6 +111,8 @@ int b200sr_last_launch_count(const b200sr_engine* e);
  * "fold_up" (1: conv_up1/up2 read the nearest-2x upsampling through the duplicated-pixel TMA view; 0: materialise it),
  * "trunk_lo" (where the residual stream's e5m2 lo part is used -- 0: in the RRDB-level skip only, 1: also in the first
  * RDB's residual add, 2: the pair after every RDB),
+ * "rdb_half64" (1: the 32-channel last chunk of RDB conv2 / conv4 is loaded as a 32-channel SWIZZLE_64B box; 0: a
+ * 64-channel box of which half is used; identical bytes),
  * "fuse_tail" (1: conv_hr + conv_last as one rolling kernel, the 4x tensor between them stays on chip; identical bytes),
  * "pair" (1: single-chunk convs run through conv3x3_sc_kernel -- resident weights, row-pair stages; 0: the per-row
  * conv3x3_tc_kernel, identical bytes), "last9" (1: conv_last with the kx taps stacked on N; 0: per-tap form, within 1 LSB),

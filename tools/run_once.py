@@ -18,6 +18,8 @@ W = int(sys.argv[3]) if len(sys.argv) > 3 else 1280
 N = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 1
 eng = B200Engine(model, make_synthetic_state_dict(model, 0), gpu_id=0)
+for k, v in [kv.split("=") for kv in os.environ.get("OPTS", "").split(",") if kv]:   # e.g. OPTS=rdb_interleave=0,trunk_lo=2
+    eng.set_option(k, int(v))
 rng = np.random.default_rng(0)
 x = torch.from_numpy(rng.integers(0, 256, size=(N, H, W, 3), dtype=np.uint8)).cuda()
 for _ in range(reps):

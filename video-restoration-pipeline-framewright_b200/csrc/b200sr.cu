@@ -43,6 +43,7 @@ struct Layer {
   std::vector<float> w, b;      // host fp32 OIHW / bias
   uint8_t* d_wpack = nullptr;   // packed bf16 image (tensor-core layers)
   uint8_t* d_wsub[4] = {nullptr, nullptr, nullptr, nullptr};   // conv_up1 / conv_up2: one image per sub-pixel phase (a, b)
+  uint8_t* d_wrdb = nullptr;    // RDB conv2 / conv4 (Cin % 64 == 32): image whose last chunk has 64-byte rows (SWIZZLE_64B)
   uint8_t* d_wlast9 = nullptr;  // conv_last: kx taps stacked on N (conv3x3_sc.cuh, EPI_LAST9_U8)
   float* d_wfirst = nullptr;    // [9][cin][64] fp32 (first layer, CUDA-core kernel)
   std::vector<float> wfirst;    // the same on the host (3-channel first layer: passed as a kernel parameter)
@@ -132,6 +133,7 @@ struct b200sr_engine {
                             // at every RRDB end, read at the next one); 1 = also in the first RDB's own residual add;
                             // 2 = the pair after EVERY RDB (rounds 1-2a)
   int opt_fuse_tail = 1;    // conv_hr + conv_last as one kernel (hr_last_fused.cuh; needs opt_pair and opt_last9)
+  int opt_half64 = 1;       // fused RDB: the 32-channel last chunk of conv2 / conv4 as a 32-channel SWIZZLE_64B box
   int opt_pair = 1;         // single-chunk convs through conv3x3_sc_kernel (resident weights, row-pair stages)
   int opt_last9 = 1;        // conv_last with the kx taps stacked on N (needs opt_pair)
   int opt_abl = 0;          // dev: timing ablations of the per-conv kernel (ConvArgs::abl); results are wrong when set
@@ -277,6 +279,34 @@ std::vector<uint8_t> pack_weights(const Layer& l) {
             const uint16_t h = l.fp16 ? f2h(v) : f2bf(v);
             memcpy(tile + off, &h, 2);
           }
+        }
+      }
+    }
+  return img;
+}
+
+// Fused-RDB image of a layer with Cin % 64 == 32 (conv2, conv4): full chunks as in pack_weights, the last chunk
+// (32 channels) with 64-byte rows, SWIZZLE_64B, at the same chunk offset -- it is copied as 3 x (3*COUTP x 64 B).
+std::vector<uint8_t> pack_weights_rdb_half(const Layer& l) {
+  std::vector<uint8_t> img = pack_weights(l);
+  const int nchunks = (l.cin + 63) / 64;
+  const int COUTP = l.coutp;
+  const size_t tile_bytes = static_cast<size_t>(3) * COUTP * 128;
+  uint8_t* chunk = img.data() + static_cast<size_t>(nchunks - 1) * 3 * tile_bytes;
+  memset(chunk, 0, 3 * tile_bytes);
+  const size_t htile = tile_bytes / 2;
+  for (int dx = 0; dx < 3; ++dx)
+    for (int blk = 0; blk < 3; ++blk) {
+      const int ky = 2 - blk;
+      for (int co = 0; co < l.cout; ++co) {
+        const int r = blk * COUTP + co;
+        for (int j = 0; j < 32; ++j) {
+          const int ci = (nchunks - 1) * 64 + j;
+          const float v = l.w[((static_cast<size_t>(co) * l.cin + ci) * 3 + ky) * 3 + dx];
+          uint32_t off = static_cast<uint32_t>(r) * 64 + (j / 8) * 16 + (j % 8) * 2;
+          off ^= ((off >> 7) & 3u) << 4;
+          const uint16_t h = l.fp16 ? f2h(v) : f2bf(v);
+          memcpy(chunk + dx * htile + off, &h, 2);
         }
       }
     }
@@ -695,6 +725,8 @@ int launch_rdb_fused(b200sr_engine* e, Lane* lane, int li, bool rrdb_end, __nv_b
   if (rc) return rc;
   CUtensorMap amap;
   if (!tmap_encode_act(&amap, Dcur, 3 * N, H, W, 64, 64, 130, 128)) return fail(e, B200SR_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  CUtensorMap amap_h;   // the first 32 channels of a plane as 64-byte rows (half chunks of conv2 / conv4)
+  if (!tmap_encode_act(&amap_h, Dcur, 3 * N, H, W, 64, 32, 130, 64)) return fail(e, B200SR_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   const size_t plane = static_cast<size_t>(N) * H * W * 64;   // elements per chunk plane
   RdbArgs a{};
   double flops = 0;
@@ -706,7 +738,7 @@ int launch_rdb_fused(b200sr_engine* e, Lane* lane, int li, bool rrdb_end, __nv_b
     c.W = W;
     c.nchunks = (l.cin + 63) / 64;
     c.last_ksteps = (l.cin % 64 == 32) ? 2 : 4;
-    c.wpack = l.d_wpack;
+    c.wpack = (e->opt_half64 && l.d_wrdb) ? l.d_wrdb : l.d_wpack;
     c.bias = l.d_bias;
     c.slope = 0.2f;
     c.in_planes = 3;
@@ -733,6 +765,7 @@ int launch_rdb_fused(b200sr_engine* e, Lane* lane, int li, bool rrdb_end, __nv_b
   a.nflags = lane->rdb_nflags;
   a.flag_target = ((W + 127) / 128) * RDB_NEPI_WARPS;
   a.rrdb_end = rrdb_end ? 1 : 0;
+  a.half64 = e->opt_half64 ? 1 : 0;
   ++lane->rdb_launch_idx;
   if (lane->rdb_launch_idx == -e->opt_rdb_stats) {   // negative: cycle counters only (no per-item / per-row stamps)
     if (!e->d_rdb_stats) CUDA_TRY(e, cudaMalloc(&e->d_rdb_stats, 296 * 16 * sizeof(long long)));
@@ -762,7 +795,7 @@ int launch_rdb_fused(b200sr_engine* e, Lane* lane, int li, bool rrdb_end, __nv_b
   ProfScope prof_scope(e, PC_RDB_FUSED, flops, st);
   CUDA_TRY(e, cudaMemsetAsync(lane->d_rdb_flags, 0, static_cast<size_t>(lane->rdb_nflags + 1) * sizeof(int), st));
   const int grid = std::min(a.nitems, e->opt_max_ctas > 0 ? e->opt_max_ctas : e->num_sms * RDB_CTAS);
-  rdb_fused_kernel<<<grid, RDB_NTHREADS, RDB_SMEM_BYTES, st>>>(amap, a);
+  rdb_fused_kernel<<<grid, RDB_NTHREADS, RDB_SMEM_BYTES, st>>>(amap, amap_h, a);
   CUDA_TRY(e, cudaGetLastError());
   lane->launches++;
   return B200SR_OK;
@@ -1183,6 +1216,7 @@ void b200sr_destroy(b200sr_engine* e) {
       if (p) cudaFree(p);
     if (l.d_wfirst) cudaFree(l.d_wfirst);
     if (l.d_wlast9) cudaFree(l.d_wlast9);
+    if (l.d_wrdb) cudaFree(l.d_wrdb);
     if (l.d_bias) cudaFree(l.d_bias);
   }
   for (auto* p : e->prelu_dev)
@@ -1254,6 +1288,11 @@ int b200sr_finalize(b200sr_engine* e) {
       if (!l.d_wpack) CUDA_TRY(e, cudaMalloc(&l.d_wpack, img.size()));
       CUDA_TRY(e, cudaMemcpy(l.d_wpack, img.data(), img.size(), cudaMemcpyHostToDevice));
       const size_t nl = e->layers.size();
+      if (e->desc.arch == B200SR_ARCH_RRDB && l.cin % 64 == 32 && l.cin > 64) {   // RDB conv2 / conv4
+        std::vector<uint8_t> himg = pack_weights_rdb_half(l);
+        if (!l.d_wrdb) CUDA_TRY(e, cudaMalloc(&l.d_wrdb, himg.size()));
+        CUDA_TRY(e, cudaMemcpy(l.d_wrdb, himg.data(), himg.size(), cudaMemcpyHostToDevice));
+      }
       if (e->desc.arch == B200SR_ARCH_RRDB && i == nl - 1) {   // conv_last: stacked-kx image
         std::vector<uint8_t> simg = pack_weights_last9(l);
         if (!l.d_wlast9) CUDA_TRY(e, cudaMalloc(&l.d_wlast9, simg.size()));
@@ -1610,6 +1649,10 @@ int b200sr_set_option(b200sr_engine* e, const char* key, int value) {
   }
   if (!strcmp(key, "trunk_lo")) {
     e->opt_trunk_lo = value;
+    return B200SR_OK;
+  }
+  if (!strcmp(key, "rdb_half64")) {
+    e->opt_half64 = value;
     return B200SR_OK;
   }
   if (!strcmp(key, "fuse_tail")) {

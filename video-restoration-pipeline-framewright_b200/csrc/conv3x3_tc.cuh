@@ -172,6 +172,15 @@ __device__ __forceinline__ void ld_global_256_ef(const void* p, uint32_t (&v)[8]
                : "memory");
 #endif
 }
+// Evict-last variant (EXPERIMENT -DB200SR_RDB_STORE_LAST: the dense-block intermediates, read again 1..7 steps later)
+#ifndef B200SR_RDB_STORE_LAST
+#define B200SR_RDB_STORE_LAST 0
+#endif
+__device__ __forceinline__ void st_global_256_el(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 // Non-volatile variant: the compiler may hoist and batch these (used for read-only / read-before-write data).
 __device__ __forceinline__ void ld_global_256_nv(const void* p, uint32_t (&v)[8]) {
   asm("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -293,7 +302,10 @@ __device__ __forceinline__ void store_bf16_row(__nv_bfloat16* dst, const float (
 #pragma unroll
       for (int i = 0; i < 8; ++i) p[i] = pack_bf16x2(v[g * 16 + 2 * i], v[g * 16 + 2 * i + 1]);
     }
-    st_global_256(dst + g * 16, p);
+    if constexpr (COUT == 32 && B200SR_RDB_STORE_LAST != 0)
+      st_global_256_el(dst + g * 16, p);
+    else
+      st_global_256(dst + g * 16, p);
   }
 }
 

@@ -1,7 +1,7 @@
 // conv_hr (64 -> 64, LeakyReLU) and conv_last (64 -> 3, clamp / quantise) of the RRDBNet HR tail as ONE kernel: the
 // 4x-resolution tensor between them (128 B per HR pixel: 1.9 GB per 720p frame written and read back) never leaves the
-// SM.  DRAM bytes are time on this part (~0.16 ms per GB of a power-capped step), and these two
-// launches moved 7.6 of the tail's 8.9 GB per frame.
+// SM.  Epilogue stores and TMA loads of that size are what the power-capped step pays for;
+// these two launches moved 7.6 of the tail's 8.9 GB per frame.
 //
 // Same arithmetic, same MMA order per accumulator and same fp16 rounding point as conv3x3_sc_kernel<64, EPI_ACT_BF16>
 // followed by conv3x3_sc_kernel<32, EPI_LAST9_U8> (identical bytes: tests/test_gpu_parity.py), organised as a ROLLING

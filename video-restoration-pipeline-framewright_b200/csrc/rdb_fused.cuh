@@ -69,6 +69,9 @@ struct RdbArgs {
   int* counter;           // next unclaimed item (zeroed before the launch): items are claimed in list order
   int nflags;             // number of completion counters (bounds of every flag index; checked in debug builds)
   int flag_target;        // counter value of a complete block: column tiles x epilogue warps
+  int half64;             // the 32-channel last chunk of conv2 / conv4 is loaded as a 32-channel TMA box (64-byte rows,
+                          // SWIZZLE_64B, tensor map `amap_h`) with a matching weight image, instead of over-reading a
+                          // 64-channel box of which only half feeds the MMAs
   int rrdb_end;           // conv5 epilogue also applies the RRDB-level skip
   long long* stats;       // optional [grid][16] cycle counters (dev tool; nullptr = off)
   long long* trace;       // optional [nitems][10] globaltimer stamps per item (dev tool; nullptr = off)
@@ -195,7 +198,8 @@ constexpr int RDB_NGRP = RDB_NEPI_WARPS / 4;                 // epilogue groups 
 constexpr int RDB_NTHREADS = 32 * (2 + RDB_NEPI_WARPS);
 
 __global__ void __launch_bounds__(RDB_NTHREADS, RDB_CTAS)
-rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ RdbArgs args) {
+rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap amap_h,
+                 const __grid_constant__ RdbArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;
@@ -236,6 +240,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
     }
     fence_mbar_init();
     tma_prefetch_desc(&amap);
+    tma_prefetch_desc(&amap_h);
   }
   if (warp == 1) {
     tmem_alloc(&s_tmem_base, RDB_TMEM_COLS);
@@ -297,16 +302,23 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
 #ifdef B200SR_ABL_NOHINT
       const uint64_t pol_item = pol_normal;
 #else
+#if defined(B200SR_RDB_INTER_LAST)   // EXPERIMENT: keep the intermediates' rows in L2 (evict_last) until conv5 has read them
+      const uint64_t pol_item = item.k == 4 ? pol_first : pol_last;
+#else
       const uint64_t pol_item = item.k == 4 ? pol_first : pol_normal;
+#endif
 #endif
       for (int c = 0; c < L.nchunks; ++c) {
         RDB_TIMED(2, mbar_wait(&bar_wempty[wb], wphase ^ 1));
+        // half chunk (conv2 / conv4, last chunk = 32 channels): 64-byte rows everywhere (weights, activation box)
+        const bool half = args.half64 && c == L.nchunks - 1 && L.last_ksteps == 2;
+        const uint32_t wt = half ? wtile / 2 : wtile;
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&bar_wfull[wb], 3 * wtile);
+          mbar_arrive_expect_tx(&bar_wfull[wb], 3 * wt);
           const uint8_t* wsrc = L.wpack + static_cast<size_t>(c) * 3 * wtile;
 #pragma unroll
           for (int d = 0; d < 3; ++d)
-            bulk_load_1d(&bar_wfull[wb], sW + wb * RDB_WBUF_BYTES + d * wtile, wsrc + d * wtile, wtile);
+            bulk_load_1d(&bar_wfull[wb], sW + wb * RDB_WBUF_BYTES + d * wt, wsrc + d * wt, wt);
         }
         __syncwarp();
         // The blocks of the predecessor conv this chunk reads (rows y0-1 .. y0+rows, at most 4 blocks) must be
@@ -368,9 +380,10 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
           RDB_TIMED(1, mbar_wait(&bar_empty[stage], phase ^ 1));
           if (lane == 0) {   // (the lane that executed the fences above)
             RDB_ASSERT(r >= -1 && r <= L.H && x0 >= -1 && x0 < L.W && c * L.N + item.n < 3 * L.N, "TMA coordinate", r, x0);
-            mbar_arrive_expect_tx(&bar_full[stage], 130 * 128);
+            mbar_arrive_expect_tx(&bar_full[stage], half ? 130 * 64 : 130 * 128);
             const int rr = (RDB_RING > 0 && c > 0 && r >= 0 && r < L.H) ? r % RDB_RING : r;
-            tma_load_4d_hint(&amap, &bar_full[stage], sA + stage * RDB_A_STAGE_BYTES, 0, x0, rr, c * L.N + item.n, pol);
+            tma_load_4d_hint(half ? &amap_h : &amap, &bar_full[stage], sA + stage * RDB_A_STAGE_BYTES, 0, x0, rr,
+                             c * L.N + item.n, pol);
           }
           __syncwarp();
           if (++stage == RDB_NSTAGES) {
@@ -395,8 +408,10 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    const uint64_t adesc0 = make_smem_desc(smem_u32(sA), 1024, SWZ_128B, 0);
-    const uint64_t bdesc0 = make_smem_desc(smem_u32(sW), 1024, SWZ_128B, 0);
+    const uint64_t adesc0_f = make_smem_desc(smem_u32(sA), 1024, SWZ_128B, 0);
+    const uint64_t bdesc0_f = make_smem_desc(smem_u32(sW), 1024, SWZ_128B, 0);
+    const uint64_t adesc0_h = make_smem_desc(smem_u32(sA), 512, SWZ_64B, 0);    // 64-byte rows (half chunks)
+    const uint64_t bdesc0_h = make_smem_desc(smem_u32(sW), 512, SWZ_64B, 0);
     int stage = 0, phase = 0, wb = 0, wphase = 0;
     uint32_t rempty_par = 0xFFFFu;   // parity to wait for, per 32-column slot (fresh barrier: parity 1 passes)
     int qi = 0, qphase = 0;
@@ -425,6 +440,11 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
         const bool first_chunk = (c == 0);
         const bool last_chunk = (c == L.nchunks - 1);
         RDB_TIMED(0, mbar_wait(&bar_wfull[wb], wphase));
+        const bool half = args.half64 && ks == 2;           // 32-channel chunk held as 64-byte rows (SWIZZLE_64B)
+        const uint32_t rb = half ? 64u : 128u;              // bytes per A / B row = stride of the kx tap views
+        const uint32_t wt = half ? wtile / 2 : wtile;       // bytes per dx tile of the weight chunk
+        const uint64_t adesc0 = half ? adesc0_h : adesc0_f;
+        const uint64_t bdesc0 = half ? bdesc0_h : bdesc0_f;
         const uint64_t bdesc_w = bdesc0 + static_cast<uint64_t>((wb * RDB_WBUF_BYTES) >> 4);
         // Two input rows (two pipeline stages) per burst: the tensor pipe buffers only a couple of instructions, so
         // every barrier wait / descriptor computation between bursts is a pipe bubble (probe_umma.cu T6: the gap
@@ -445,7 +465,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             stg[j] = (stage + j) & (RDB_NSTAGES - 1);
             dcol[j] = tmem_base + static_cast<uint32_t>((yy - 1 + blk_lo) * cout);
             ad0[j] = adesc0 + static_cast<uint64_t>((stg[j] * RDB_A_STAGE_BYTES) >> 4);
-            bd0[j] = bdesc_w + static_cast<uint64_t>((blk_lo * cout * 128) >> 4);
+            bd0[j] = bdesc_w + static_cast<uint64_t>((blk_lo * cout * rb) >> 4);
             idn[j] = nblk == 3 ? idesc3 : (nblk == 2 ? idesc2 : idesc1);
             if (newr[j]) {
               for (int sl = (yy + 1) * spr; sl < (yy + 2) * spr; ++sl) {
@@ -465,7 +485,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
                 if (newr[j]) {
                   if (nblk_[j] > 1) umma_bf16(dcol[j], ad0[j], bd0[j], nblk_[j] == 3 ? idesc2 : idesc1, 1);
                   umma_bf16(dcol[j] + (nblk_[j] - 1) * cout, ad0[j],
-                            bd0[j] + static_cast<uint64_t>(((nblk_[j] - 1) * cout * 128) >> 4), idesc1, 0);
+                            bd0[j] + static_cast<uint64_t>(((nblk_[j] - 1) * cout * rb) >> 4), idesc1, 0);
                 } else {
                   umma_bf16(dcol[j], ad0[j], bd0[j], idn[j], 1);
                 }
@@ -480,8 +500,8 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
 #pragma unroll
                   for (int i = 1; i < 6; ++i) {
                     const int dx = i >> 1, k = i & 1;
-                    umma_bf16(dcol[j], ad0[j] + static_cast<uint64_t>((dx * 128 + k * 32) >> 4),
-                              bd0[j] + static_cast<uint64_t>((dx * wtile + k * 32) >> 4), idn[j], 1);
+                    umma_bf16(dcol[j], ad0[j] + static_cast<uint64_t>((dx * rb + k * 32) >> 4),
+                              bd0[j] + static_cast<uint64_t>((dx * wt + k * 32) >> 4), idn[j], 1);
                   }
                 }
                 umma_commit(&bar_empty[stg[j]]);
@@ -577,8 +597,8 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
                     next_ready = ok;
                   }
                   const int dx = i >> 1, k = i & 1;
-                  umma_bf16(dc, ad + static_cast<uint64_t>((dx * 128 + k * 32) >> 4),
-                            bdesc_w + static_cast<uint64_t>((dx * wtile + k * 32) >> 4), idesc3, 1);
+                  umma_bf16(dc, ad + static_cast<uint64_t>((dx * rb + k * 32) >> 4),
+                            bdesc_w + static_cast<uint64_t>((dx * wt + k * 32) >> 4), idesc3, 1);
                 }
               }
               umma_commit(&bar_empty[j ? s1 : s0]);
