@@ -787,15 +787,28 @@ int launch_rdb_fused(b200sr_engine* e, Lane* lane, int li, bool rrdb_end, __nv_b
     CUDA_TRY(e, cudaMemsetAsync(e->d_rdb_trace2, 0, static_cast<size_t>(lane->rdb_nitems) * 48 * sizeof(long long), st));
     a.trace2 = e->d_rdb_trace2;
   }
-  static bool attr_done[16] = {};
-  if (!attr_done[e->device & 15]) {
-    CUDA_TRY(e, cudaFuncSetAttribute(rdb_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RDB_SMEM_BYTES));
-    attr_done[e->device & 15] = true;
+  // conv5's epilogue is specialised at compile time (rdb_fused.cuh, MODE): RRDB end | lo part read | lo part written
+  const int mode = (rrdb_end ? RDB_MODE_RRDB_END : 0) | (a.L[4].lo_in != nullptr ? RDB_MODE_LO_IN : 0) |
+                   (a.L[4].lo_out != nullptr ? RDB_MODE_LO_OUT : 0);
+  using RdbKernel = void (*)(const CUtensorMap, const CUtensorMap, const RdbArgs);
+  RdbKernel kern = nullptr;
+  switch (mode) {   // the combinations option trunk_lo = 0 / 1 / 2 produces
+    case 0: kern = rdb_fused_kernel<0>; break;
+    case 2: kern = rdb_fused_kernel<2>; break;
+    case 5: kern = rdb_fused_kernel<5>; break;
+    case 6: kern = rdb_fused_kernel<6>; break;
+    case 7: kern = rdb_fused_kernel<7>; break;
+    default: return fail(e, B200SR_ERR_STATE, "fused RDB: no kernel for residual-stream mode " + std::to_string(mode));
+  }
+  static bool attr_done[16][8] = {};
+  if (!attr_done[e->device & 15][mode]) {
+    CUDA_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RDB_SMEM_BYTES));
+    attr_done[e->device & 15][mode] = true;
   }
   ProfScope prof_scope(e, PC_RDB_FUSED, flops, st);
   CUDA_TRY(e, cudaMemsetAsync(lane->d_rdb_flags, 0, static_cast<size_t>(lane->rdb_nflags + 1) * sizeof(int), st));
   const int grid = std::min(a.nitems, e->opt_max_ctas > 0 ? e->opt_max_ctas : e->num_sms * RDB_CTAS);
-  rdb_fused_kernel<<<grid, RDB_NTHREADS, RDB_SMEM_BYTES, st>>>(amap, amap_h, a);
+  kern<<<grid, RDB_NTHREADS, RDB_SMEM_BYTES, st>>>(amap, amap_h, a);
   CUDA_TRY(e, cudaGetLastError());
   lane->launches++;
   return B200SR_OK;

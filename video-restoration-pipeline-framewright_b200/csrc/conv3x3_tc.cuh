@@ -188,6 +188,18 @@ __device__ __forceinline__ void ld_global_256_nv(const void* p, uint32_t (&v)[8]
       : "l"(p));
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// B200SR_EPI_XPOSE (fused RDB kernel epilogues, full 128-pixel column tiles; same bytes in memory).  The per-pixel threads
+// of a warp touch 32 DIFFERENT cache lines per 32-byte vector store (pixel pitch 128 B).  With the switch the lanes
+// (2i, 2i+1) = pixels (x, x+1) exchange one of each two 32-byte blocks through the register file, so that every store
+// instruction covers 64 CONTIGUOUS bytes per lane pair: 16 lines and half the L1 -> L2 requests per instruction, for
+// 8 SHFL + 24 SEL per 64 bytes.  bit 0: conv1-4's 64 bytes per pixel (-0.4 % step time, four A/B pairs on two boxes);
+// bit 1: conv5's 128 bytes of hi where the output is hi alone (another -0.1..-0.5 %, at the noise level).  Output bytes
+// identical.  The same trick on conv5's hi LOADS lost 9 % (shuffles on the epilogue's critical path), and on the stores of
+// the un-specialised epilogue 3.4 % (register spills at the 168-register cap): profiles/r02c_epi_xpose_ab.txt.
+#ifndef B200SR_EPI_XPOSE
+#define B200SR_EPI_XPOSE 3
+#endif
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -241,7 +253,9 @@ __device__ __forceinline__ uint32_t f32x4_e5m2(float a, float b, float c, float 
   return p01 | (p23 << 16);
 }
 // Splits 64 fp32 values into the pair and stores it: hi -> NHWC bf16 `hi_dst` (64 channels), lo -> `lo_dst`.
-__device__ __forceinline__ void store_trunk_pair(__nv_bfloat16* hi_dst, uint8_t* lo_dst, const float (&v)[64]);
+template <bool LO_OUT = true>
+__device__ __forceinline__ void store_trunk_pair(__nv_bfloat16* hi_dst, uint8_t* lo_dst, const float (&v)[64],
+                                                 bool xp = false, int pitch = 0);
 __device__ __forceinline__ uint8_t quant_u8(float v) {
   v = fminf(fmaxf(v, 0.f), 1.f);
   return static_cast<uint8_t>(__float2int_rn(v * 255.0f));
@@ -290,8 +304,42 @@ __device__ __forceinline__ void load_acc_row(uint32_t taddr, float (&acc)[COUT])
   }
 }
 
+// B200SR_EPI_XPOSE: stores the two 32-byte blocks `b` of this lane's pixel (`dst` = its first block, `pitch` = bytes to
+// pixel x + 1) in the pair-coalesced order.  All 32 lanes must call it (shuffles); lane parity = pixel parity.
+template <int HINT = 0>   // 1: L2::evict_first
+__device__ __forceinline__ void store_blocks_paired(uint8_t* dst, ptrdiff_t pitch, const uint32_t (&b)[2][8]) {
+  const bool odd = (threadIdx.x & 1) != 0;
+  uint32_t r[8], dE[8], dO[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = __shfl_xor_sync(0xffffffffu, odd ? b[0][i] : b[1][i], 1);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    dE[i] = odd ? r[i] : b[0][i];    // the even lane's pixel: block 0 (own) | block 1 (received)
+    dO[i] = odd ? b[1][i] : r[i];    // the odd lane's pixel:  block 0 (received) | block 1 (own)
+  }
+  if constexpr (HINT == 1) {
+    st_global_256_ef(odd ? dst - pitch + 32 : dst, dE);
+    st_global_256_ef(odd ? dst + 32 : dst + pitch, dO);
+  } else {
+    st_global_256(odd ? dst - pitch + 32 : dst, dE);
+    st_global_256(odd ? dst + 32 : dst + pitch, dO);
+  }
+}
+
 template <int COUT>
-__device__ __forceinline__ void store_bf16_row(__nv_bfloat16* dst, const float (&v)[COUT], int fp16 = 0) {
+__device__ __forceinline__ void store_bf16_row(__nv_bfloat16* dst, const float (&v)[COUT], int fp16 = 0, bool xp = false,
+                                               int pitch = 0) {
+  if constexpr (COUT == 32 && (B200SR_EPI_XPOSE & 1) != 0) {
+    if (xp) {   // warp-uniform: a full column tile of the fused RDB kernel (bf16 intermediates)
+      uint32_t b[2][8];
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b[g][i] = pack_bf16x2(v[g * 16 + 2 * i], v[g * 16 + 2 * i + 1]);
+      store_blocks_paired(reinterpret_cast<uint8_t*>(dst), static_cast<ptrdiff_t>(pitch) * 2, b);
+      return;
+    }
+  }
 #pragma unroll
   for (int g = 0; g < COUT / 16; ++g) {
     uint32_t p[8];
@@ -309,7 +357,32 @@ __device__ __forceinline__ void store_bf16_row(__nv_bfloat16* dst, const float (
   }
 }
 
-__device__ __forceinline__ void store_trunk_pair(__nv_bfloat16* hi_dst, uint8_t* lo_dst, const float (&v)[64]) {
+// LO_OUT = false (fused RDB kernel, compile-time): the stream leaves as hi alone -- no rounding residual is computed.
+// xp (warp-uniform, B200SR_EPI_XPOSE bit 1): the 128 bytes of hi leave as pair-coalesced stores (store_blocks_paired).
+template <bool LO_OUT>
+__device__ __forceinline__ void store_trunk_pair(__nv_bfloat16* hi_dst, uint8_t* lo_dst, const float (&v)[64], bool xp,
+                                                 int pitch) {
+  if constexpr (!LO_OUT) {
+    if ((B200SR_EPI_XPOSE & 2) != 0 && xp) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {   // 64 bytes of the pixel at a time
+        uint32_t b[2][8];
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) b[g][i] = pack_bf16x2(v[(2 * k + g) * 16 + 2 * i], v[(2 * k + g) * 16 + 2 * i + 1]);
+        store_blocks_paired<1>(reinterpret_cast<uint8_t*>(hi_dst) + k * 64, static_cast<ptrdiff_t>(pitch) * 2, b);
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t p[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[i] = pack_bf16x2(v[g * 16 + 2 * i], v[g * 16 + 2 * i + 1]);
+        st_global_256_ef(hi_dst + g * 16, p);
+      }
+    }
+  } else {
   float r[64];   // residual after the bf16 rounding
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -334,16 +407,19 @@ __device__ __forceinline__ void store_trunk_pair(__nv_bfloat16* hi_dst, uint8_t*
     }
     st_global_256_ef(lo_dst + g * LO_GSTRIDE, p);
   }
+  }   // LO_OUT
 }
 
 // The RDB tail of one pixel.  `hi`/`lo` hold the pixel's x pair (RDB input) as loaded from hi_in / lo_in:
 //   x = hi + lo ; v = (acc + b) * 0.2 + x ; RRDB end: v = v * 0.2 + (x0.hi + x0.lo) ; result stored as a pair.
 // Shared by the per-conv kernel and the fused RDB kernel so that both produce the same bits.
-template <bool RRDB>
+// LO_IN / LO_OUT = false (the fused RDB kernel's compile-time modes): the RDB input / output is hi alone -- `lo` is not
+// read (x = hi + 0, the same bits as decoding all-zero lo bytes) / no residual is split off.
+template <bool RRDB, bool LO = true, bool LO_OUT = true>
 __device__ __forceinline__ void trunk_pixel(const ConvArgs& a, const float* s_bias, float (&acc)[64],
                                             const uint32_t (&hi)[4][8], const uint32_t (&lo)[2][8],
                                             const uint32_t (&h0)[4][8], const uint32_t (&l0)[2][8], int n, int y,
-                                            int x) {
+                                            int x, bool xp = false) {
   const size_t pix = (static_cast<size_t>(n) * a.H + y) * a.W + x;
   const size_t loff = lo_off(n, y, x, a.H, a.W);
 #pragma unroll
@@ -351,13 +427,14 @@ __device__ __forceinline__ void trunk_pixel(const ConvArgs& a, const float* s_bi
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float lf[4], l0f[4];
-      e5m2x4_f32(lo[g][i], lf);
+      if constexpr (LO) e5m2x4_f32(lo[g][i], lf);
       if constexpr (RRDB) e5m2x4_f32(l0[g][i], l0f);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c = g * 32 + i * 4 + j;
         const uint32_t hw = hi[c >> 4][(c & 15) >> 1];
-        const float xv = ((c & 1) ? bf16hi_f32(hw) : bf16lo_f32(hw)) + lf[j];
+        // (!LO: "+ 0.f" stays -- the same bits as decoding all-zero lo bytes, also for x = -0; dropping it measured flat)
+        const float xv = ((c & 1) ? bf16hi_f32(hw) : bf16lo_f32(hw)) + (LO ? lf[j] : 0.f);
         float v = (acc[c] + s_bias[c]) * 0.2f + xv;
         if constexpr (RRDB) {
           const uint32_t h0w = h0[c >> 4][(c & 15) >> 1];
@@ -366,13 +443,17 @@ __device__ __forceinline__ void trunk_pixel(const ConvArgs& a, const float* s_bi
         acc[c] = v;
       }
     }
-  store_trunk_pair(a.out + pix * a.out_pitch + a.out_choff, a.lo_out ? a.lo_out + loff : nullptr, acc);
+  store_trunk_pair<LO_OUT>(a.out + pix * a.out_pitch + a.out_choff, (LO_OUT && a.lo_out) ? a.lo_out + loff : nullptr, acc,
+                           xp, a.out_pitch);
 }
 // one pixel's pair (64 channels) from an NHWC hi tensor + the tile-interleaved lo bytes
+// (LO = false, the fused RDB kernel's compile-time modes: the stream is hi alone and `lo` is left untouched)
+template <bool LO = true>
 __device__ __forceinline__ void load_trunk_pair(const __nv_bfloat16* hi_px, const uint8_t* lo_px, uint32_t (&hi)[4][8],
                                                 uint32_t (&lo)[2][8]) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) ld_global_256_ef(hi_px + g * 16, hi[g]);
+  if constexpr (!LO) return;
   if (lo_px != nullptr) {
 #pragma unroll
     for (int g = 0; g < 2; ++g) ld_global_256_ef(lo_px + g * LO_GSTRIDE, lo[g]);
@@ -394,7 +475,7 @@ __device__ __forceinline__ void store_sample(const ConvArgs& a, size_t px3, int 
 // Fused pointwise tail of one output pixel (one thread).
 template <int COUT, int EPI>
 __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* s_bias, const float* s_prelu,
-                                               float (&acc)[COUT], int n, int y, int x) {
+                                               float (&acc)[COUT], int n, int y, int x, bool xp = false) {
   const size_t pix = (static_cast<size_t>(n) * a.H + y) * a.W + x;
   if constexpr (EPI == EPI_ACT_BF16) {
 #pragma unroll
@@ -403,7 +484,7 @@ __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* s
       acc[c] = v > 0.f ? v : v * a.slope;
     }
     const size_t opix = a.sub ? (static_cast<size_t>(n) * (2 * a.H) + (2 * y + a.sub_a)) * (2 * a.W) + (2 * x + a.sub_b) : pix;
-    store_bf16_row<COUT>(a.out + opix * a.out_pitch + a.out_choff, acc, a.out_fp16);
+    store_bf16_row<COUT>(a.out + opix * a.out_pitch + a.out_choff, acc, a.out_fp16, xp, a.out_pitch);
   } else if constexpr (EPI == EPI_PRELU_BF16) {
 #pragma unroll
     for (int c = 0; c < COUT; ++c) {

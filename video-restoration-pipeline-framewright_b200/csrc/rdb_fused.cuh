@@ -197,9 +197,17 @@ constexpr int RDB_NEPI_WARPS = RDB_CTAS == 1 ? 8 : 4;
 constexpr int RDB_NGRP = RDB_NEPI_WARPS / 4;                 // epilogue groups (one warp per TMEM lane quarter each)
 constexpr int RDB_NTHREADS = 32 * (2 + RDB_NEPI_WARPS);
 
+// MODE (compile time; the launch picks the instantiation, b200sr.cu::launch_rdb_fused) describes conv5's epilogue:
+// bit 0 = RRDB end (args.rrdb_end), bit 1 = the RDB input carries a lo part (L[4].lo_in != nullptr), bit 2 = the output
+// does (L[4].lo_out != nullptr).  With the default residual format two of the three launches of an RRDB are MODE 0 --
+// hi in, hi out: no e5m2 decode, no rounding residual, 48 fewer live registers -- and the third is MODE 5.
+constexpr int RDB_MODE_RRDB_END = 1, RDB_MODE_LO_IN = 2, RDB_MODE_LO_OUT = 4;
+template <int MODE>
 __global__ void __launch_bounds__(RDB_NTHREADS, RDB_CTAS)
 rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap amap_h,
                  const __grid_constant__ RdbArgs args) {
+  constexpr bool RRDB_END = (MODE & RDB_MODE_RRDB_END) != 0, LO_IN = (MODE & RDB_MODE_LO_IN) != 0,
+                 LO_OUT = (MODE & RDB_MODE_LO_OUT) != 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;
@@ -654,6 +662,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
       const ConvArgs& L = args.L[item.k];
       const int n = item.n;
       const int x = item.tx * 128 + m;
+      const bool xp = B200SR_EPI_XPOSE != 0 && item.tx * 128 + 128 <= L.W;   // pair-coalesced stores: full tiles only
       if (item.k == 4) {
         // pull the residual (lo) rows of this item towards L2 while the MMAs run (2 groups x 1 KB per warp-row); the
         // x.hi rows arrive with the chunk-0 TMA loads.  At the RRDB end also x0.lo of the RRDB input pair (last
@@ -662,8 +671,8 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
           const size_t o = lo_off(n, item.y0 + Y, item.tx * 128 + q * 32, L.H, L.W) + (lane & 7) * 128 +
                            static_cast<size_t>((lane >> 3) & 1) * LO_GSTRIDE;
           if (lane < 16) {
-            if (L.lo_in) prefetch_l2(L.lo_in + o);
-            if (args.rrdb_end) prefetch_l2(L.xb_lo + o);
+            if constexpr (LO_IN) prefetch_l2(L.lo_in + o);
+            if constexpr (RRDB_END) prefetch_l2(L.xb_lo + o);
           }
         }
         for (int Y = 0; Y < item.rows; ++Y) {
@@ -676,10 +685,10 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             const size_t pix = (static_cast<size_t>(n) * L.H + item.y0 + Y) * L.W + x;
             const size_t loff = lo_off(n, item.y0 + Y, x < L.W ? x : 0, L.H, L.W);
             if (x < L.W) {
-              if (args.rrdb_end)
-                load_trunk_pair(L.xb_hi + pix * L.out_pitch, L.xb_lo + loff, ph, pl);
+              if constexpr (RRDB_END)
+                load_trunk_pair<true>(L.xb_hi + pix * L.out_pitch, L.xb_lo + loff, ph, pl);
               else
-                load_trunk_pair(L.hi_in + pix * L.out_pitch, L.lo_in ? L.lo_in + loff : nullptr, ph, pl);
+                load_trunk_pair<LO_IN>(L.hi_in + pix * L.out_pitch, L.lo_in + loff, ph, pl);
             }
             RDB_TIMED(0, mbar_wait(&bar_rfull[sl], (rfull_par >> sl) & 1u));
             if (q == 2 && lane == 0) RDB_STAMP2(it, Y, 1);
@@ -694,12 +703,12 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             }
             RDB_TIMED(2, {
               if (x < L.W && !(B200SR_ABL_NOEPI & 2)) {
-                if (args.rrdb_end) {
+                if constexpr (RRDB_END) {
                   uint32_t xh[4][8], xl[2][8];
-                  load_trunk_pair(L.hi_in + pix * L.out_pitch, L.lo_in ? L.lo_in + loff : nullptr, xh, xl);
-                  trunk_pixel<true>(L, s_bias[4], acc, xh, xl, ph, pl, n, item.y0 + Y, x);
+                  load_trunk_pair<LO_IN>(L.hi_in + pix * L.out_pitch, L.lo_in + loff, xh, xl);
+                  trunk_pixel<true, LO_IN, LO_OUT>(L, s_bias[4], acc, xh, xl, ph, pl, n, item.y0 + Y, x, xp);
                 } else {
-                  trunk_pixel<false>(L, s_bias[4], acc, ph, pl, ph, pl, n, item.y0 + Y, x);
+                  trunk_pixel<false, LO_IN, LO_OUT>(L, s_bias[4], acc, ph, pl, ph, pl, n, item.y0 + Y, x, xp);
                 }
               }
             });
@@ -733,7 +742,7 @@ rdb_fused_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             RDB_TIMED(5, {
               if (x < L.W && !(B200SR_ABL_NOEPI & 1))
                 epilogue_pixel<32, EPI_ACT_BF16>(L, s_bias[item.k], s_bias[item.k], acc, n,
-                                                 RDB_RING > 0 ? (item.y0 + Y) % RDB_RING : item.y0 + Y, x);
+                                                 RDB_RING > 0 ? (item.y0 + Y) % RDB_RING : item.y0 + Y, x, xp);
             });
             RDB_COUNT(6, 1);
             if (q == 2 && lane == 0) RDB_STAMP2(it, Y, 2);
