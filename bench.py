@@ -383,7 +383,7 @@ def run_b200(args):
     # DRAM traffic of the dominant kernel, per launch, from the committed `ncu --set full` capture of this command's
     # kernel at the same frames-per-launch (profiles/r0x_rdb_fused_traffic.json; null if the batch differs)
     traffic = None
-    for tname in ("r02b_rdb_fused_traffic.json", "r02_rdb_fused_traffic.json", "r01_rdb_fused_traffic.json"):
+    for tname in ("r02d_rdb_fused_traffic.json", "r02b_rdb_fused_traffic.json", "r02_rdb_fused_traffic.json"):
         tpath = os.path.join(ROOT, "profiles", tname)
         if dom == "rdb_fused" and os.path.exists(tpath):
             with open(tpath) as f:
