@@ -36,6 +36,10 @@ def test_claim_table_shards_and_steals_from_the_back():
     assert t.claim(0, 4) == [0, 1, 2] and t.claim(0, 4) == []
     t.set_avail(5)
     assert t.claim(1, 4) == [] and t.claim(0, 4) == [3, 4]
+    t.set_avail(9)                                 # front = 0: shard 1's worker draws from the FRONT of shard 0 ...
+    assert t.claim(1, 2, steal=False, front=0) == [5, 6] and t.claim(0, 2) == [7, 8]
+    assert t.held_by(1) == [5, 6]                  # ... and holds what it took in its own row
+    assert t.claim(1, 2, steal=False, front=0) == []
 
 
 def test_every_frame_once_with_per_frame_callbacks(pool):
@@ -106,6 +110,22 @@ def test_stream_is_ordered_and_bounded(pool):
     assert sorted(res.ok) == list(range(n))
     assert [g[0] for g in got] == list(range(n))                      # emitted in order
     assert all(v == i and shp == (2 * h, 2 * w, 3) for i, v, shp in got)
+
+
+def test_stream_is_shared_by_all_gpus(pool):
+    """Ring mode is self-scheduling: every GPU takes the next chunk from the front of the one ordered stream, so a
+    slow GPU 0 (the stand-in engine sleeps 4 ms per frame there) leaves most of the stream to the other two."""
+    n, h, w = 120, 8, 10
+    frames = [np.full((h, w, 3), i % 251, np.uint8) for i in range(n)]
+    got = []
+    cfg = dict(CFG, tile_pad=4)
+    res = pool.stream(iter(frames), cfg, lambda i, out: got.append((i, int(out[0, 0, 0]))), num_frames=n,
+                      frame_shape=(h, w), scale=2, batch=2, window=12, engine_factory=fake_engine)
+    assert sorted(res.ok) == list(range(n)) and not res.errors
+    assert got == [(i, i % 251) for i in range(n)]                    # still strictly in order
+    per_gpu = {g: len(v) for g, v in res.frames_per_gpu.items()}
+    assert per_gpu[1] + per_gpu[2] > n // 2, per_gpu
+    assert per_gpu[1] > 0 and per_gpu[2] > 0, per_gpu
 
 
 def test_files_in_files_out_and_unreadable_frame(pool, tmp_path):

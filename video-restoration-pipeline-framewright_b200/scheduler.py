@@ -316,14 +316,17 @@ class ClaimTable:
         with self.lock:
             return sum(max(0, self.cur[2 * g + 1] - self.cur[2 * g]) for g in range(self.num_shards))
 
-    def claim(self, shard: int, batch: int, steal: bool = True) -> List[int]:
-        """Up to `batch` consecutive indices: from the front of the own shard, else from the back of the fullest one."""
+    def claim(self, shard: int, batch: int, steal: bool = True, front: Optional[int] = None) -> List[int]:
+        """Up to `batch` consecutive indices: from the front of the own shard, else from the back of the fullest one.
+        `front` names the shard whose FRONT this worker draws from instead of its own (ring mode: every GPU takes the
+        next chunk of the one ordered stream); what it takes is still recorded in its own row of the held-table."""
         with self.lock:
             av = self.avail.value
-            lo, hi = self.cur[2 * shard], min(self.cur[2 * shard + 1], av)
+            src = shard if front is None else front
+            lo, hi = self.cur[2 * src], min(self.cur[2 * src + 1], av)
             if lo < hi:
                 k = min(batch, hi - lo)
-                self.cur[2 * shard] = lo + k
+                self.cur[2 * src] = lo + k
                 idxs = list(range(lo, lo + k))
                 self._hold(shard, idxs)
                 return idxs
@@ -354,6 +357,7 @@ class JobSpec:
     batch: int = 2
     shard_of_gpu: Dict[int, int] = field(default_factory=dict)
     steal: bool = True
+    front_shard: Optional[int] = None      # ring mode: every worker claims from the front of this shard
     fail_on_gpus: Tuple[int, ...] = ()     # test hook: these GPUs report every frame as failed
     crash_on_gpus: Tuple[int, ...] = ()    # test hook: these workers die (os._exit) after their first claim
     engine_factory: Optional[Callable[[Dict[str, Any]], Any]] = None   # test hook: object with enhance_batch / enhance
@@ -468,7 +472,7 @@ def _worker_main(gpu_id: int, cmd_q, results, retry_q, claims: ClaimTable, job_d
                 except queue_mod.Empty:
                     pass
                 if not idxs:
-                    idxs = claims.claim(shard, spec.batch, steal=spec.steal)
+                    idxs = claims.claim(shard, spec.batch, steal=spec.steal, front=spec.front_shard)
                 if not idxs:
                     time.sleep(0.002)
                     continue
@@ -564,9 +568,9 @@ class SchedulerPool:
             frame_callback: Optional[Callable[[int, str, bool, Optional[str], int], None]] = None,
             shard_ranges: Optional[Sequence[Tuple[int, int]]] = None, steal: bool = True,
             avail: Optional[int] = None, feeder: Optional[Callable[["SchedulerPool", Dict[str, Any]], None]] = None,
-            **hooks) -> RunResult:
+            front_shard: Optional[int] = None, **hooks) -> RunResult:
         """Runs one job to completion.  `shard_ranges[k]` is the contiguous index range GPU k starts from (default:
-        `multi_gpu.shard_range`); `avail` + `feeder` implement the ordered ring mode of `stream`."""
+        `multi_gpu.shard_range`); `avail` + `feeder` + `front_shard` implement the ordered ring mode of `stream`."""
         from .multi_gpu import shard_range
 
         with self._lock:
@@ -587,7 +591,7 @@ class SchedulerPool:
                 shard_ranges = [shard_range(n, len(alive), k) for k in range(len(alive))]
             shard_of_gpu = {g: k for k, g in enumerate(alive)}
             owner_of = {}
-            for k, (lo, hi) in enumerate(shard_ranges):
+            for k, (lo, hi) in enumerate(shard_ranges if front_shard is None else []):   # (ring mode: no owners)
                 for i in range(lo, hi):
                     owner_of[i] = alive[k] if k < len(alive) else alive[0]
             self._claims.reset(list(shard_ranges), n if avail is None else avail)
@@ -597,7 +601,7 @@ class SchedulerPool:
                     self._retry.get_nowait()
                 except queue_mod.Empty:
                     break
-            spec = JobSpec(job_id, source, sink, dict(config), int(batch), shard_of_gpu, steal, **hooks)
+            spec = JobSpec(job_id, source, sink, dict(config), int(batch), shard_of_gpu, steal, front_shard, **hooks)
             for g in alive:
                 self._cmd[g].put(("job", spec))
             in_flight: Dict[int, set] = {g: set() for g in self.gpu_ids}
@@ -754,10 +758,12 @@ class SchedulerPool:
                 frame_callback(i, name, ok, err, gpu)
 
         try:
-            # one shared shard [0, N): every GPU takes the next chunk of the stream (self-scheduling, in order)
+            # one shared shard [0, N): every GPU takes the next chunk from its FRONT (self-scheduling, in order; at most
+            # `window` frames are ever available, so the GPUs work on neighbouring chunks of the stream)
             ranges = [(0, num_frames)] + [(0, 0)] * (len(self.gpu_ids) - 1)
             res = self.run(_SingleShard(src), sink, config, batch=batch, progress_callback=progress_callback,
-                           frame_callback=on_frame, shard_ranges=ranges, steal=True, avail=0, feeder=feeder, **hooks)
+                           frame_callback=on_frame, shard_ranges=ranges, steal=False, avail=0, feeder=feeder,
+                           front_shard=0, **hooks)
         finally:
             ring_in.release()
             ring_out.release()
@@ -786,7 +792,7 @@ class SchedulerPool:
 
 
 class _SingleShard(FrameSource):
-    """Wraps a source for ring mode (all GPUs draw from shard 0; stealing from its back is disabled by `avail`)."""
+    """Wraps a source for ring mode (all GPUs draw from the front of shard 0: `front_shard`)."""
 
     def __init__(self, inner: FrameSource):
         self.inner = inner
