@@ -74,7 +74,10 @@ def test_failed_frames_are_retried_on_another_gpu(pool):
     from framewright_b200.scheduler import ChecksumSink
 
     n = 24
-    res = pool.run(CountingSource(n), ChecksumSink(), CFG, batch=2, engine_factory=fake_engine, fail_on_gpus=(1,))
+    # (steal=False: GPU 1's shard can only be claimed by GPU 1, so it certainly fails frames -- with stealing the
+    # other two may empty its shard before its runner threads have started)
+    res = pool.run(CountingSource(n), ChecksumSink(), CFG, batch=2, engine_factory=fake_engine, fail_on_gpus=(1,),
+                   steal=False)
     assert sorted(res.ok) == list(range(n)) and not res.errors
     assert res.retried and not res.frames_per_gpu[1]
     res = pool.run(CountingSource(6), ChecksumSink(), CFG, batch=1, engine_factory=fake_engine,
@@ -126,6 +129,34 @@ def test_stream_is_shared_by_all_gpus(pool):
     per_gpu = {g: len(v) for g, v in res.frames_per_gpu.items()}
     assert per_gpu[1] + per_gpu[2] > n // 2, per_gpu
     assert per_gpu[1] > 0 and per_gpu[2] > 0, per_gpu
+
+
+def test_stream_that_ends_early_does_not_hang(pool):
+    """A pipe that delivers fewer frames than announced (container metadata is often off by a few): the frames that
+    arrived are emitted in order, the rest is reported as failed, `stream` returns."""
+    n, have, h, w = 25, 10, 8, 10
+    frames = [np.full((h, w, 3), i, np.uint8) for i in range(have)]
+    got = []
+    res = pool.stream(iter(frames), CFG, lambda i, out: got.append(i), num_frames=n, frame_shape=(h, w), scale=2,
+                      batch=2, window=8, engine_factory=fake_engine)
+    assert got == list(range(have)) and sorted(res.ok) == list(range(have))
+    assert sorted(res.errors) == list(range(have, n)) and "ended after 10 of 25" in res.errors[n - 1]
+    bad = [np.zeros((h, w, 3), np.uint8), np.zeros((h + 1, w, 3), np.uint8)]          # a frame of the wrong size
+    res = pool.stream(iter(bad), CFG, lambda i, out: None, num_frames=2, frame_shape=(h, w), scale=2, batch=1,
+                      window=4, engine_factory=fake_engine)
+    assert sorted(res.ok) == [0] and "failed at frame 1" in res.errors[1]
+
+
+def test_exception_in_a_callback_ends_the_job_and_leaves_the_pool_usable(pool):
+    from framewright_b200.scheduler import ChecksumSink
+
+    def boom(i, name, ok, err, gpu):
+        raise BrokenPipeError("encoder went away")
+
+    with pytest.raises(BrokenPipeError):
+        pool.run(CountingSource(30), ChecksumSink(), CFG, batch=2, engine_factory=fake_engine, frame_callback=boom)
+    res = pool.run(CountingSource(20), ChecksumSink(), CFG, batch=2, engine_factory=fake_engine)
+    assert sorted(res.ok) == list(range(20)) and not res.errors
 
 
 def test_files_in_files_out_and_unreadable_frame(pool, tmp_path):

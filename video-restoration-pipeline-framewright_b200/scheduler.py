@@ -646,71 +646,89 @@ class SchedulerPool:
                     final(i, False, err, gpu, None)
 
             last_heard = {g: time.time() for g in self.gpu_ids}
-            while done_count < n:
-                try:
-                    m = self._results.get(timeout=0.25)
-                except queue_mod.Empty:
-                    m = None
-                if m is not None and len(m) > 2 and m[1] == job_id and m[0] in ("claim", "worker_error"):
-                    last_heard[m[2]] = time.time()
-                elif m is not None and m[0] == "done" and m[1] == job_id:
-                    last_heard[m[5]] = time.time()
-                for g, p in self._procs.items():   # hung worker: alive, holding frames, silent for too long
-                    if (g not in dead_seen and p.is_alive() and time.time() - last_heard[g] > self.stall_timeout
-                            and (in_flight[g] or (g in shard_of_gpu and self._claims.held_by(shard_of_gpu[g])))):
-                        logger.error("worker for GPU %s is silent for %.0f s: terminating it", g, self.stall_timeout)
-                        p.terminate()
-                        p.join(timeout=10)
-                if m is not None and len(m) > 1 and m[1] == job_id:
-                    if m[0] == "claim":
-                        in_flight[m[2]].update(i for i in m[3] if i not in finished)
-                    elif m[0] == "done":
-                        _, _, i, ok, err, gpu, info = m
-                        in_flight[gpu].discard(i)
-                        if ok:
-                            final(i, True, None, gpu, info)
-                        elif i not in finished:
-                            failed(i, err or "Unknown error", gpu)
-                    elif m[0] == "worker_error":
-                        _, _, gpu, err = m
-                        logger.error("GPU %s cannot run the job: %s", gpu, err)
-                        dead_seen.add(gpu)
-                        res.dead_gpus.append(gpu)
-                        state["last_error"] = err
-                # liveness: a dead worker never reports -- fail what it had claimed (retried elsewhere)
-                for g, p in self._procs.items():
-                    if g not in dead_seen and not p.is_alive():
-                        dead_seen.add(g)
-                        res.dead_gpus.append(g)
-                        logger.error("worker for GPU %s died (exit code %s)", g, p.exitcode)
-                        lost = set(in_flight[g])
-                        if g in shard_of_gpu:
-                            lost.update(self._claims.held_by(shard_of_gpu[g]))
-                        for i in sorted(lost):
-                            if i not in finished:
-                                failed(i, f"worker for GPU {g} died (exit code {p.exitcode})", g)
-                        in_flight[g].clear()
-                usable = [g for g in self.alive_gpus() if g not in dead_seen]
-                if not usable:
-                    why = state.get("last_error") or "No GPUs available"
-                    for i in range(n):
-                        if i not in finished:
-                            final(i, False, why, -1, None)
-            self._job_done.set()
-            if feeder_thread is not None:
-                feeder_thread.join(timeout=5)
-            exited, deadline = set(), time.time() + 30
-            want = set(g for g in alive if self._procs[g].is_alive() and g not in res.dead_gpus) | \
-                set(g for g in res.dead_gpus if self._procs[g].is_alive())
-            while exited < want and time.time() < deadline:
-                try:
-                    m = self._results.get(timeout=0.25)
-                    if m[0] == "job_exit" and m[1] == job_id:
-                        exited.add(m[2])
-                except queue_mod.Empty:
-                    want = set(g for g in want if self._procs[g].is_alive())
-            res.total_time = time.time() - t0
+            try:
+                self._run_loop(n, job_id, res, state, in_flight, finished, dead_seen, last_heard, shard_of_gpu, final,
+                               failed, lambda: done_count)
+            finally:
+                # whatever happened (also an exception from a caller's callback): end the job in the workers, so that
+                # the pool stays usable and no runner thread keeps claiming frames of a job nobody waits for
+                self._job_done.set()
+                if feeder_thread is not None:
+                    feeder_thread.join(timeout=5)
+                exited, deadline = set(), time.time() + 30
+                want = set(g for g in alive if self._procs[g].is_alive() and g not in res.dead_gpus) | \
+                    set(g for g in res.dead_gpus if self._procs[g].is_alive())
+                while exited < want and time.time() < deadline:
+                    try:
+                        m = self._results.get(timeout=0.25)
+                        if m[0] == "job_exit" and m[1] == job_id:
+                            exited.add(m[2])
+                    except queue_mod.Empty:
+                        want = set(g for g in want if self._procs[g].is_alive())
+                res.total_time = time.time() - t0
             return res
+
+    def _run_loop(self, n, job_id, res, state, in_flight, finished, dead_seen, last_heard, shard_of_gpu, final, failed,
+                  done) -> None:
+        """The parent's side of one job: completion messages, hung / dead workers, an input that ended early."""
+        while done() < n:
+            try:
+                m = self._results.get(timeout=0.25)
+            except queue_mod.Empty:
+                m = None
+            if m is not None and len(m) > 2 and m[1] == job_id and m[0] in ("claim", "worker_error"):
+                last_heard[m[2]] = time.time()
+            elif m is not None and m[0] == "done" and m[1] == job_id:
+                last_heard[m[5]] = time.time()
+            for g, p in self._procs.items():   # hung worker: alive, holding frames, silent for too long
+                if (g not in dead_seen and p.is_alive() and time.time() - last_heard[g] > self.stall_timeout
+                        and (in_flight[g] or (g in shard_of_gpu and self._claims.held_by(shard_of_gpu[g])))):
+                    logger.error("worker for GPU %s is silent for %.0f s: terminating it", g, self.stall_timeout)
+                    p.terminate()
+                    p.join(timeout=10)
+            if m is not None and len(m) > 1 and m[1] == job_id:
+                if m[0] == "claim":
+                    in_flight[m[2]].update(i for i in m[3] if i not in finished)
+                elif m[0] == "done":
+                    _, _, i, ok, err, gpu, info = m
+                    in_flight[gpu].discard(i)
+                    if ok:
+                        final(i, True, None, gpu, info)
+                    elif i not in finished:
+                        failed(i, err or "Unknown error", gpu)
+                elif m[0] == "worker_error":
+                    _, _, gpu, err = m
+                    logger.error("GPU %s cannot run the job: %s", gpu, err)
+                    dead_seen.add(gpu)
+                    res.dead_gpus.append(gpu)
+                    state["last_error"] = err
+            # liveness: a dead worker never reports -- fail what it had claimed (retried elsewhere)
+            for g, p in self._procs.items():
+                if g not in dead_seen and not p.is_alive():
+                    dead_seen.add(g)
+                    res.dead_gpus.append(g)
+                    logger.error("worker for GPU %s died (exit code %s)", g, p.exitcode)
+                    lost = set(in_flight[g])
+                    if g in shard_of_gpu:
+                        lost.update(self._claims.held_by(shard_of_gpu[g]))
+                    for i in sorted(lost):
+                        if i not in finished:
+                            failed(i, f"worker for GPU {g} died (exit code {p.exitcode})", g)
+                    in_flight[g].clear()
+            usable = [g for g in self.alive_gpus() if g not in dead_seen]
+            if not usable:
+                why = state.get("last_error") or "No GPUs available"
+                for i in range(n):
+                    if i not in finished:
+                        final(i, False, why, -1, None)
+            # ring mode: the input ended (or failed) before `num_frames` frames -- the rest can never arrive
+            cut = state.get("truncate")
+            if cut is not None and not state.get("truncated"):
+                state["truncated"] = True
+                logger.warning(cut[1])
+                for i in range(cut[0], n):
+                    if i not in finished:
+                        final(i, False, cut[1], -1, None)
 
     # ---- frame-array in / frame-array out, ordered, bounded memory
     def stream(self, frames, config: Dict[str, Any], emit: Callable[[int, np.ndarray], None], num_frames: int,
@@ -740,6 +758,10 @@ class SchedulerPool:
                     f = next(it)
                     a[i % S][...] = f
                 except StopIteration:
+                    state["truncate"] = (i, f"input stream ended after {i} of {num_frames} frames")
+                    return
+                except Exception as e:   # a frame of the wrong shape, a broken pipe: the job must still end
+                    state["truncate"] = (i, f"input stream failed at frame {i}: {type(e).__name__}: {e}")
                     return
                 pool._claims.set_avail(i + 1)
 
