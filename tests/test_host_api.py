@@ -209,6 +209,55 @@ def test_sr_backend_dir_api_batches_and_collects_failures(tmp_path, monkeypatch)
     assert empty.warnings == ["No frames found"]
 
 
+def test_sr_backend_dir_api_recovers_after_out_of_memory(tmp_path, monkeypatch):
+    """One frame runs the device out of memory: it fails with the reference's 'GPU out of memory ... Try: 1) ...' text,
+    the upsampler cache is cleared (the engine is destroyed), and the FOLLOWING frames get a fresh upsampler instead of
+    failing on the closed one."""
+    import cv2
+
+    from framewright_b200.engine import EngineOutOfMemory
+
+    ind = tmp_path / "in"
+    ind.mkdir()
+    for i in range(6):
+        cv2.imwrite(str(ind / f"frame_{i:08d}.png"), np.full((8, 8, 3), 66 if i == 1 else 10 * i, np.uint8))
+
+    class _Up(_BatchUpsampler):
+        closed = False
+
+        def _check(self, frames):
+            if self.closed:
+                raise RuntimeError("upsampler is closed")
+            if (np.asarray(frames)[..., 0, 0, 0] == 66).any():
+                raise EngineOutOfMemory("GPU out of memory: workspace")
+
+        def enhance_batch(self, frames, out=None):
+            self._check(frames)
+            return np.repeat(np.repeat(frames, 4, axis=1), 4, axis=2)
+
+        def enhance(self, img, outscale=None):
+            self._check(img[None])
+            return np.repeat(np.repeat(img, 4, axis=0), 4, axis=1), "RGB"
+
+    made = []
+
+    def get(cfg):
+        if not made or made[-1].closed:
+            made.append(_Up())
+        return made[-1]
+
+    def clear():
+        made[-1].closed = True
+
+    monkeypatch.setattr(srm, "get_upsampler", get)
+    monkeypatch.setattr(srm, "clear_upsampler_cache", clear)
+    res = srm.B200RealESRGANBackend().upscale_frames(ind, tmp_path / "out", 4)
+    assert (res.frames_processed, res.frames_failed) == (5, 1) and len(made) == 2
+    assert len(res.warnings) == 1 and res.warnings[0].startswith("Frame frame_00000001.png: GPU out of memory")
+    assert "Try: 1) Reduce tile_size" in res.warnings[0]
+    assert sorted(p.name for p in (tmp_path / "out").glob("*.png")) == [f"frame_{i:08d}.png" for i in (0, 2, 3, 4, 5)]
+
+
 def test_super_resolution_facade_selects_falls_back_and_processes_lists(monkeypatch):
     """`SuperResolution` (reference :1194-1527): auto selection, fallback from a backend that does not exist here,
     `process(frames: List)` batching runs of same-size frames, `upscale_frame`, factories."""

@@ -242,7 +242,7 @@ class B200RealESRGANBackend(SRBackend):
                 return str(e)
 
         try:
-            upsampler = get_upsampler(cfg)
+            get_upsampler(cfg)
         except Exception as e:   # engine / weights unavailable: every frame fails with that message
             for p in frames:
                 finished(p, str(e))
@@ -263,13 +263,16 @@ class B200RealESRGANBackend(SRBackend):
                 nonlocal peak_vram
                 if not batch:
                     return
-                plain = all(im.ndim == 3 and im.shape[2] == 3 and im.dtype == np.uint8 for _, im in batch) \
-                    and float(scale) == float(upsampler.scale)
                 try:
+                    # (looked up per batch: after an out-of-memory failure the cache is cleared -- the engine is gone --
+                    # and the next batch gets a fresh one, as the reference's per-frame get_upsampler does)
+                    up = get_upsampler(cfg)
+                    plain = all(im.ndim == 3 and im.shape[2] == 3 and im.dtype == np.uint8 for _, im in batch) \
+                        and float(scale) == float(up.scale)
                     if plain and len(batch) > 1:
-                        outs = upsampler.enhance_batch(np.stack([im for _, im in batch]))
+                        outs = up.enhance_batch(np.stack([im for _, im in batch]))
                     else:
-                        outs = [upsampler.enhance(im, outscale=scale)[0] for _, im in batch]
+                        outs = [up.enhance(im, outscale=scale)[0] for _, im in batch]
                 except EngineOutOfMemory as e:
                     if len(batch) > 1:                      # smaller launches first, then give up frame by frame
                         for item in batch:
