@@ -188,3 +188,64 @@ def test_video_restorer_enhance_stage_runs_verbatim_against_the_mirror(tmp_path,
     assert ok is False and ("vram" in err.lower() or "memory" in err.lower())         # restorer.py:1746's test
     assert not validate_frame_integrity(tmp_path / "o2.png").is_valid
     mine.clear_upsampler_cache()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_reference_ensemble_member_runs_through_the_mirror(tmp_path, monkeypatch):
+    """`EnsembleSR`'s Real-ESRGAN member (`processors/ensemble_sr.py:132-223`, the reference file loaded
+    unmodified) -- `ModelProcessor("realesrgan").process_frame(frame)` builds a `PyTorchESRGANConfig`, calls
+    `get_upsampler` and then `enhance_frame_pytorch(frame, upsampler, config)` with an ndARRAY: through the mirror that
+    returns the upscaled frame (checked against the oracle)."""
+    import torch
+
+    from framewright_b200 import pytorch_realesrgan as mine
+    from framewright_b200 import upsampler as up_mod
+    from framewright_b200.archs import make_synthetic_state_dict
+    from oracle import oracle
+
+    class OracleEngine:
+        def __init__(self, arch, state_dict, gpu_id=0):
+            self.name = next(k for k, v in up_mod.MODEL_ARCHS.items() if v == arch)
+            self.sd = state_dict
+
+        def upscale_host(self, frames, out=None, tile=0, tile_pad=10, pre_pad=0):
+            return oracle.make_upsampler(self.name, self.sd, tile=tile, tile_pad=tile_pad, pre_pad=pre_pad).enhance(frames)[0]
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(up_mod, "B200Engine", OracleEngine)
+    monkeypatch.setattr(mine, "is_pytorch_esrgan_available", lambda: True)
+    monkeypatch.setattr(mine, "_auto_tile", lambda gpu: 0)
+    monkeypatch.setattr(mine, "MODEL_SCALES", dict(mine.MODEL_SCALES))
+    wdir = tmp_path / "weights"
+    wdir.mkdir()
+    # (the member asks for RealESRGAN_x4plus: a 1-block file under that name would not load strictly, so the 23-block
+    # synthetic network it is -- on a 12 x 16 frame the oracle takes a few seconds)
+    sd = make_synthetic_state_dict("RealESRGAN_x4plus", 0)
+    torch.save({"params_ema": sd}, str(wdir / "RealESRGAN_x4plus.pth"))
+    monkeypatch.setenv("B200SR_WEIGHTS_DIR", str(wdir))
+    mine.clear_upsampler_cache()
+
+    saved = {k: v for k, v in sys.modules.items() if k == "framewright" or k.startswith("framewright.")}
+    try:
+        for name, path in [("framewright", REF), ("framewright.processors", REF + "/processors")]:
+            m = types.ModuleType(name)
+            m.__path__ = [path]
+            monkeypatch.setitem(sys.modules, name, m)
+        monkeypatch.setitem(sys.modules, "framewright.processors.pytorch_realesrgan", mine)
+        monkeypatch.setattr(sys, "dont_write_bytecode", True)
+        ens = importlib.import_module("framewright.processors.ensemble_sr")
+        member = ens.ModelProcessor("realesrgan", gpu_id=0)
+        assert member.load()
+        frame = oracle.synthetic_frame(12, 16, seed=9, kind="mixed")
+        out = member.process_frame(frame)
+        assert isinstance(out, np.ndarray) and out.shape == (48, 64, 3) and out.dtype == np.uint8
+        ref, _ = oracle.make_upsampler("RealESRGAN_x4plus", sd, tile=0, pre_pad=0).enhance(frame)
+        assert np.array_equal(out, ref)
+        assert member.process_frame(np.zeros((4, 4, 5), np.uint8)) is None      # engine error -> None, as the caller expects
+    finally:
+        mine.clear_upsampler_cache()
+        for k in [k for k in sys.modules if k == "framewright" or k.startswith("framewright.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

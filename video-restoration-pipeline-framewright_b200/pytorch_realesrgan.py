@@ -189,7 +189,17 @@ def enhance_frame_pytorch(
     output_path: Path,
     config: PyTorchESRGANConfig,
 ) -> Tuple[bool, Optional[str]]:
-    """Enhance one frame file -> file.  Returns (success, error_message); never raises."""
+    """Enhance one frame file -> file.  Returns (success, error_message); never raises.
+
+    Frame-array form: the reference's `EnsembleSR` member (`processors/ensemble_sr.py:206-211`) calls this function as
+    `enhance_frame_pytorch(frame, upsampler, config)` with a BGR ndarray and the object `get_upsampler` returned, and
+    uses the return value as the upscaled frame.  (Against the reference's own function that call can only fail --
+    it `imread`s `str(frame)`.)  Here it does what the caller means: ndarray in -> upscaled ndarray out through that
+    upsampler, exceptions propagating to the caller's `try`, which turns them into `None`."""
+    if isinstance(input_path, np.ndarray):
+        config.validate()
+        upsampler = output_path if hasattr(output_path, "enhance") else get_upsampler(config)
+        return upsampler.enhance(input_path, outscale=config.scale_factor)[0]
     try:
         import cv2
 
