@@ -121,8 +121,12 @@ def _reference_method(path, cls, name):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
-def test_video_restorer_enhance_stage_runs_verbatim_against_the_mirror(tmp_path, monkeypatch):
-    """`VideoRestorer._enhance_single_frame_pytorch` (restorer.py:1420-1460) -- the reference's caller,
+@pytest.mark.parametrize("ref_file,ref_cls", [("restorer.py", "VideoRestorer"),
+                                              ("mixins/frame_processing.py", "FrameProcessingMixin")])
+def test_video_restorer_enhance_stage_runs_verbatim_against_the_mirror(tmp_path, monkeypatch, ref_file, ref_cls):
+    """(Both copies of the caller: `VideoRestorer`'s own method and the `FrameProcessingMixin` one, which imports the
+    processor module and the validator relatively inside the method -- resolved here to the mirrors.)
+    SURVEY 8 a10: `VideoRestorer._enhance_single_frame_pytorch` (restorer.py:1420-1460) -- the reference's caller,
     its source text unmodified -- executed against this repo's module functions: ncnn model name -> config ->
     `enhance_frame_pytorch` -> output validation, returning `(output_path, ok, err)`; and the "memory" error string
     its retry ladder greps for (:1746)."""
@@ -169,7 +173,15 @@ def test_video_restorer_enhance_stage_runs_verbatim_against_the_mirror(tmp_path,
           "is_pytorch_esrgan_available": mine.is_pytorch_esrgan_available,
           "convert_ncnn_model_name": mine.convert_ncnn_model_name, "PyTorchESRGANConfig": mine.PyTorchESRGANConfig,
           "enhance_frame_pytorch": mine.enhance_frame_pytorch, "validate_frame_integrity": validate_frame_integrity}
-    exec(_reference_method(os.path.join(REF, "restorer.py"), "VideoRestorer", "_enhance_single_frame_pytorch"), ns)
+    if ref_cls == "FrameProcessingMixin":      # its `from ..processors.pytorch_realesrgan import ...` / `from ..validators import ...`
+        ns.update(__package__="framewright.mixins", __name__="framewright.mixins.frame_processing")
+        for name in ("framewright", "framewright.mixins", "framewright.processors", "framewright.validators"):
+            m = types.ModuleType(name)
+            m.__path__ = []
+            monkeypatch.setitem(sys.modules, name, m)
+        monkeypatch.setitem(sys.modules, "framewright.processors.pytorch_realesrgan", mine)
+        sys.modules["framewright.validators"].validate_frame_integrity = validate_frame_integrity
+    exec(_reference_method(os.path.join(REF, ref_file), ref_cls, "_enhance_single_frame_pytorch"), ns)
     restorer = types.SimpleNamespace(config=types.SimpleNamespace(model_name="realesrgan-x4plus-anime", scale_factor=4,
                                                                   gpu_id=None))
     img = oracle.synthetic_frame(20, 24, seed=5, kind="mixed")
