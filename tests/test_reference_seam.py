@@ -261,3 +261,91 @@ def test_reference_ensemble_member_runs_through_the_mirror(tmp_path, monkeypatch
         for k in [k for k in sys.modules if k == "framewright" or k.startswith("framewright.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_reference_sr_facade_with_the_b200_operator_registered(tmp_path, monkeypatch):
+    """SURVEY 8 a9 / INTEGRATION.md layer 2, on the UNMODIFIED reference `processors/enhancement/super_resolution.py`:
+    (1) its own `RealESRGANBackend` runs over the module mirror (`..pytorch_realesrgan` -> this repo's functions);
+    (2) with `B200RealESRGANBackend` registered the way INTEGRATION.md shows (module global + `BACKENDS` entries) the
+    reference's `SuperResolution` facade selects it, and `upscale_frame` / `process` / `upscale` (frames dir) give the
+    oracle's pixels."""
+    import cv2
+    import torch
+
+    from framewright_b200 import pytorch_realesrgan as mine
+    from framewright_b200 import super_resolution as my_sr
+    from framewright_b200 import upsampler as up_mod
+    from framewright_b200.archs import make_synthetic_state_dict
+    from oracle import oracle
+
+    class OracleEngine:
+        def __init__(self, arch, state_dict, gpu_id=0):
+            self.name = next(k for k, v in up_mod.MODEL_ARCHS.items() if v == arch)
+            self.sd = state_dict
+
+        def upscale_host(self, frames, out=None, tile=0, tile_pad=10, pre_pad=0):
+            up = oracle.make_upsampler(self.name, self.sd, tile=tile, tile_pad=tile_pad, pre_pad=pre_pad)
+            if frames.ndim == 4:      # the frames-dir path batches same-size frames
+                return np.stack([up.enhance(f)[0] for f in frames])
+            return up.enhance(frames)[0]
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(up_mod, "B200Engine", OracleEngine)
+    for mod in (mine, my_sr):
+        monkeypatch.setattr(mod, "is_pytorch_esrgan_available", lambda: True)
+    monkeypatch.setattr(mine, "_auto_tile", lambda gpu: 0)
+    monkeypatch.setattr(mine, "_available_vram_mb", lambda gpu: 50000.0)
+    wdir = tmp_path / "weights"
+    wdir.mkdir()
+    name = "RealESRGAN_x4plus_anime_6B"
+    sd = make_synthetic_state_dict(name, 0)
+    torch.save({"params_ema": sd}, str(wdir / (name + ".pth")))
+    monkeypatch.setenv("B200SR_WEIGHTS_DIR", str(wdir))
+    mine.clear_upsampler_cache()
+    frame = oracle.synthetic_frame(16, 20, seed=11, kind="mixed")
+    want = oracle.make_upsampler(name, sd, tile=0, pre_pad=0).enhance(frame)[0]
+
+    saved = {k: v for k, v in sys.modules.items() if k == "framewright" or k.startswith("framewright.")}
+    try:
+        for mname, path in [("framewright", REF), ("framewright.processors", REF + "/processors"),
+                            ("framewright.processors.enhancement", REF + "/processors/enhancement")]:
+            m = types.ModuleType(mname)
+            m.__path__ = [path]
+            monkeypatch.setitem(sys.modules, mname, m)
+        monkeypatch.setitem(sys.modules, "framewright.processors.pytorch_realesrgan", mine)
+        monkeypatch.setattr(sys, "dont_write_bytecode", True)
+        sr = importlib.import_module("framewright.processors.enhancement.super_resolution")
+        hw = types.SimpleNamespace(tier=None, vram_free_mb=180000, gpu_vendor=None)
+
+        # (1) the reference's own operator over the module mirror
+        ref_backend = sr.RealESRGANBackend(sr.SRConfig(scale=4), hw, "anime")
+        assert ref_backend.is_available()
+        assert np.array_equal(ref_backend.upscale_frame(frame, 4), want)
+        ind = tmp_path / "in"
+        ind.mkdir()
+        for i in range(3):
+            cv2.imwrite(str(ind / f"frame_{i + 1:08d}.png"), frame)
+        res = ref_backend.upscale_frames(ind, tmp_path / "out_ref", 4)
+        assert (res.frames_processed, res.frames_failed) == (3, 0)
+        assert np.array_equal(cv2.imread(str(tmp_path / "out_ref" / "frame_00000002.png")), want)
+
+        # (2) INTEGRATION.md layer 2: the B200 operator registered in the reference facade
+        monkeypatch.setattr(sr, "RealESRGANBackend", my_sr.B200RealESRGANBackend)
+        for key in ("realesrgan_x2", "realesrgan_x4", "realesrgan_anime"):
+            monkeypatch.setitem(sr.SuperResolution.BACKENDS, key, my_sr.B200RealESRGANBackend)
+        facade = sr.SuperResolution(sr.SRConfig(scale=4, backend="realesrgan_anime"), hw)
+        assert isinstance(facade.backend, my_sr.B200RealESRGANBackend) and facade.backend.name == "realesrgan_anime"
+        assert np.array_equal(facade.upscale_frame(frame), want)
+        outs = facade.process([frame, frame])
+        assert len(outs) == 2 and all(np.array_equal(o, want) for o in outs)
+        res = facade.upscale(ind, tmp_path / "out_b200")
+        assert (res.frames_processed, res.frames_failed, res.backend_used) == (3, 0, "realesrgan_anime")
+        assert np.array_equal(cv2.imread(str(tmp_path / "out_b200" / "frame_00000003.png")), want)
+    finally:
+        mine.clear_upsampler_cache()
+        for k in [k for k in sys.modules if k == "framewright" or k.startswith("framewright.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
