@@ -349,3 +349,100 @@ def test_reference_sr_facade_with_the_b200_operator_registered(tmp_path, monkeyp
         for k in [k for k in sys.modules if k == "framewright" or k.startswith("framewright.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_reference_streaming_pipeline_with_the_b200_enhancer(tmp_path, monkeypatch):
+    """the UNMODIFIED `StreamingPipeline` (`processors/streaming.py:815-1175`: extract / enhance / write
+    threads, bounded buffers, batches of `batch_size` `PipelineFrame`s) with `make_streaming_enhancer(...)` as its
+    `set_enhancer` function: every frame comes out processed, in the files the write stage names, with the stand-in
+    engine's pixels; an unreadable frame is skipped by the reference's write stage, not fatal."""
+    import cv2
+
+    from framewright_b200.pytorch_realesrgan import PyTorchESRGANConfig
+    from framewright_b200.restorer_adapter import make_streaming_enhancer
+    from sched_helpers import fake_engine
+
+    saved = {k: v for k, v in sys.modules.items() if k == "framewright" or k.startswith("framewright.")}
+    try:
+        for mname, path in [("framewright", REF), ("framewright.processors", REF + "/processors"),
+                            ("framewright.utils", REF + "/utils")]:
+            m = types.ModuleType(mname)
+            m.__path__ = [path]
+            monkeypatch.setitem(sys.modules, mname, m)
+        monkeypatch.setattr(sys, "dont_write_bytecode", True)
+        st = importlib.import_module("framewright.processors.streaming")
+        ind, outd = tmp_path / "in", tmp_path / "out"
+        ind.mkdir()
+        n = 11
+        for i in range(n):
+            cv2.imwrite(str(ind / f"frame_{i:08d}.png"), np.full((6, 8, 3), 10 * i, np.uint8))
+        (ind / f"frame_{n:08d}.png").write_bytes(b"not a png")
+        batches, prog = [], []
+        pipe = st.StreamingPipeline(st.StreamingConfig(batch_size=4, max_buffer_size=6, cleanup_between_chunks=False))
+        pipe.set_enhancer(make_streaming_enhancer(PyTorchESRGANConfig(model_name="RealESRGAN_x2plus", scale_factor=2),
+                                                  upsampler=fake_engine({"gpu_id": 1}), output_dir=outd))
+        pipe.set_batch_callback(lambda r: batches.append(list(r.frame_indices)))
+        paths = pipe.process(ind, outd, progress_callback=lambda f, m: prog.append(f))
+        assert paths == [outd / f"frame_{i:08d}.png" for i in range(n)]            # the unreadable frame is skipped
+        assert batches == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 10, 11]] and prog[-1] == 1.0
+        for i in range(n):
+            got = cv2.imread(str(paths[i]))
+            assert got.shape == (12, 16, 3) and int(got[0, 0, 0]) == 10 * i
+        assert not (outd / f"frame_{n:08d}.png").exists()
+    finally:
+        for k in [k for k in sys.modules if k == "framewright" or k.startswith("framewright.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_reference_multi_gpu_processor_calls_the_b200_process_func(monkeypatch):
+    """`MultiGPUProcessor.process_frames` + `_process_single_frame`
+    (`infrastructure/gpu/distributor.py:687-786`, source text unmodified; the module itself needs a GPU backend to
+    initialise) with `make_process_func(config)` as the `process_func(frame, device_id)` operator: per-GPU executor
+    threads, results sorted by frame index, an engine error becomes `ProcessingResult(success=False)`."""
+    import logging
+    import threading
+    import time
+    from concurrent.futures import ThreadPoolExecutor, as_completed
+    from typing import Callable, List, Optional
+
+    from framewright_b200 import pytorch_realesrgan as mine
+    from framewright_b200.restorer_adapter import ProcessingResult, make_process_func
+    from sched_helpers import FakeUpsampler
+
+    made = {}
+
+    class Up(FakeUpsampler):
+        def enhance(self, img, outscale=None):
+            if img.ndim not in (2, 3):
+                raise ValueError("img must be an HxW or HxWxC ndarray")      # what RealESRGANer.enhance raises
+            return super().enhance(img, outscale)
+
+    def fake_get_upsampler(cfg):
+        return made.setdefault(cfg.gpu_id, Up({"gpu_id": cfg.gpu_id}))
+
+    monkeypatch.setattr(mine, "get_upsampler", fake_get_upsampler)
+    ns = {"np": np, "time": time, "logger": logging.getLogger("ref"), "ProcessingResult": ProcessingResult,
+          "as_completed": as_completed, "List": List, "Optional": Optional, "Callable": Callable}
+    path = os.path.join(REF, "infrastructure/gpu/distributor.py")
+    exec(_reference_method(path, "MultiGPUProcessor", "process_frames"), ns)
+    exec(_reference_method(path, "MultiGPUProcessor", "_process_single_frame"), ns)
+    n = 9
+    plan = types.SimpleNamespace(frame_assignments={i: i % 2 for i in range(n)})
+    stats = types.SimpleNamespace(errors=0, times=[], update_timing=lambda t: None)
+    self = types.SimpleNamespace(
+        _initialized=True, _executors={0: ThreadPoolExecutor(1), 1: ThreadPoolExecutor(1)},
+        distributor=types.SimpleNamespace(get_optimal_distribution=lambda k: plan, _stats={0: stats, 1: stats}))
+    self._process_single_frame = lambda *a: ns["_process_single_frame"](self, *a)
+    frames = [np.full((4, 6, 3), i, np.uint8) for i in range(n - 1)] + [np.zeros((4, 6, 5, 1, 1), np.uint8)]
+    seen = []
+    fn = make_process_func(mine.PyTorchESRGANConfig(model_name="RealESRGAN_x2plus", scale_factor=2))
+    results = ns["process_frames"](self, frames, fn, callback=lambda r: seen.append(r.frame_index))
+    for ex in self._executors.values():
+        ex.shutdown()
+    assert [r.frame_index for r in results] == list(range(n)) and sorted(seen) == list(range(n))
+    assert [r.device_id for r in results] == [i % 2 for i in range(n)] and sorted(made) == [0, 1]
+    assert all(r.success and r.output.shape == (8, 12, 3) and int(r.output[0, 0, 0]) == r.frame_index for r in results[:-1])
+    assert results[-1].success is False and results[-1].error and stats.errors == 1

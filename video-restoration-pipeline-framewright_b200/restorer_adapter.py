@@ -8,9 +8,10 @@ f2  `enhance_frames_batched`: what `VideoRestorer.enhance_frames` / `_enhance_fr
     `get_adaptive_tile_sequence`), `continue_on_error` (copy the original frame so the video still assembles) and the
     `ErrorReport` bookkeeping.
 f4  `make_streaming_enhancer` -> the `enhance_fn(List[PipelineFrame]) -> List[PipelineFrame]` that
-    `StreamingPipeline.set_enhancer` takes (`processors/streaming.py:876-885`); `multi_gpu_process_frames` -> the
-    `MultiGPUProcessor.process_frames(frames, process_func, callback)` call shape
-    (`infrastructure/gpu/distributor.py:687-752`) over the scheduler's shared-memory transport.
+    `StreamingPipeline.set_enhancer` takes (`processors/streaming.py:876-885`); `make_process_func` -> the
+    `process_func(frame, device_id)` the reference's own `MultiGPUProcessor.process_frames` calls
+    (`infrastructure/gpu/distributor.py:687-752`); `multi_gpu_process_frames` -> the same call shape over the
+    scheduler's worker processes and shared-memory transport.
 f1  `RawVideoReader` / `RawVideoWriter`: raw bgr24 frame pipes (what `ffmpeg -f rawvideo -pix_fmt bgr24 -` produces /
     consumes) and `upscale_raw_stream`, the decode -> engine -> encode path with no PNG round trip and no per-frame
     `ffprobe` (`restorer.py:1109-1118, 3001-3027`, `validators.py:165-181`).
@@ -208,11 +209,18 @@ def validate_frame_integrity(frame_path: Path) -> FrameValidation:
 
 # ------------------------------------------------------------------------------------------------ f4
 def make_streaming_enhancer(config: PyTorchESRGANConfig, load: Optional[Callable[[Path], np.ndarray]] = None,
-                            upsampler: Any = None) -> Callable[[List[Any]], List[Any]]:
+                            upsampler: Any = None, output_dir: Optional[Path] = None) -> Callable[[List[Any]], List[Any]]:
     """`enhance_fn` for `StreamingPipeline.set_enhancer`: takes the pipeline's chunk of `PipelineFrame`s (`.index`,
     `.path`, `.data`, `.processed`, `.error`), runs every run of same-size frames as one engine batch, and returns the
-    same objects with `.data` replaced by the upscaled frame and `.processed` set."""
+    same objects with `.data` replaced by the upscaled frame and `.processed` set.
+    `output_dir`: also write every upscaled frame to `output_dir/frame_<index:08d>.png` -- the paths the reference's
+    write stage returns (`streaming.py:1088-1090`) but does not itself fill ("in real implementation, this would save
+    enhanced data")."""
     from .pytorch_realesrgan import get_upsampler
+
+    if output_dir is not None:
+        output_dir = Path(output_dir)
+        output_dir.mkdir(parents=True, exist_ok=True)
 
     def _load(p: Path) -> np.ndarray:
         import cv2
@@ -252,6 +260,13 @@ def make_streaming_enhancer(config: PyTorchESRGANConfig, load: Optional[Callable
                     frames[k].data = outs[k - i]
                     frames[k].processed = True
                     frames[k].error = None
+                    if output_dir is not None:
+                        import cv2
+
+                        dst = output_dir / f"frame_{frames[k].index:08d}.png"
+                        if not cv2.imwrite(str(dst), outs[k - i]) or not dst.exists():
+                            frames[k].processed = False
+                            frames[k].error = "Output file was not created"
             except Exception as e:
                 for k in range(i, j):
                     frames[k].error = str(e)
@@ -270,6 +285,27 @@ class ProcessingResult:
     output: Optional[np.ndarray] = None
     error: Optional[str] = None
     elapsed_seconds: float = 0.0
+
+
+def make_process_func(config: PyTorchESRGANConfig) -> Callable[[np.ndarray, int], np.ndarray]:
+    """The `process_func(frame, device_id) -> processed_frame` that the reference's own
+    `MultiGPUProcessor.process_frames` / `process_batch` (`infrastructure/gpu/distributor.py:687-752, 788-`) call from
+    their per-GPU executor threads: the upscaling operator on GPU `device_id` (one cached upsampler per GPU, thread-safe;
+    a [N,H,W,3] stack -- `process_batch` -- runs as one engine batch).  Exceptions propagate: the reference turns them
+    into `ProcessingResult(success=False, error=str(e))`."""
+    import dataclasses
+
+    from .pytorch_realesrgan import get_upsampler
+
+    config.validate()
+
+    def process_func(frame: np.ndarray, device_id: int) -> np.ndarray:
+        up = get_upsampler(dataclasses.replace(config, gpu_id=int(device_id)))
+        if isinstance(frame, np.ndarray) and frame.ndim == 4:
+            return up.enhance_batch(frame)
+        return up.enhance(frame, outscale=config.scale_factor)[0]
+
+    return process_func
 
 
 def multi_gpu_process_frames(frames: List[np.ndarray], config: PyTorchESRGANConfig, pool: Any = None,
