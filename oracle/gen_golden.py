@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """Generates tests/golden/*.npz from the CPU oracle (oracle/oracle.py) -- TEST INFRASTRUCTURE.
 
-PARITY UNPINNED: these vectors are produced by the oracle itself (the reference's own dependencies are not
+These vectors are produced by the ORACLE ITSELF (regression vectors: the reference's own dependencies are not
 installable here and its tests hold no vectors for this path, see oracle/oracle.py); they pin the oracle and
-the synthetic-weight recipe against drift and give the GPU tests a CPU-free comparison target.
+the synthetic-weight recipe against drift and give the GPU tests a CPU-free comparison target.  The REFERENCE-made
+vectors (the RRDBNet network through the reference's in-tree ESRGAN generator) are oracle/ref_pin.py's,
+under tests/golden/reference_made/.
 
     python oracle/gen_golden.py          # rewrites tests/golden/
 """

@@ -3,7 +3,8 @@
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` leg may
 import this module; the product package never does (and fails loudly without its CUDA library).
 
-PARITY UNPINNED.  The reference (`/root/reference/src/framewright/processors/pytorch_realesrgan.py`)
+PARITY: the RRDBNet NETWORK is PINNED to reference-made vectors; `RealESRGANer` pre / tile / post-processing
+and `SRVGGNetCompact` are UNPINNED.  The reference (`/root/reference/src/framewright/processors/pytorch_realesrgan.py`)
 does not contain the arithmetic of this path: it constructs and calls two third-party PyPI
 packages -- `basicsr` (class `RRDBNet`; last release 1.4.2) and `realesrgan` (classes `RealESRGANer`,
 `SRVGGNetCompact`; last release 0.3.0) -- which the reference neither vendors, pins nor declares
@@ -20,7 +21,13 @@ anchored on the reference's call sites:
                                      (scale, model, tile, tile_pad, pre_pad, half, gpu_id)
   * the call                         pytorch_realesrgan.py:223  `upsampler.enhance(img, outscale=scale)`
   * PSNR definition                  metrics.py:433-458
-The committed fixtures under tests/golden/ are outputs of THIS oracle (generator:
+What the reference DOES carry is one in-tree ESRGAN generator, `processors/aesrgan_face.py:171-268`
+(`ResidualDenseBlock`, `RRDB`, `AESRGAN`: the same trunk and upsampling tail, upstream's parameter names; its
+attention gate is the identity at the constructed gamma = 0).  `oracle/ref_pin.py` imports that file unmodified,
+loads the same checkpoints into it and commits what it computes (`tests/golden/reference_made/*.npz`);
+`tests/test_reference_pin.py` holds `RRDBNet` below to those vectors (x4plus, anime_6B, the x2plus network incl.
+`pixel_unshuffle` against torch's own) -- in this container bit for bit against the module run live.
+The other committed fixtures, tests/golden/*.npz, are outputs of THIS oracle (generator:
 oracle/gen_golden.py), i.e. regression vectors, not reference-made vectors.
 """
 from __future__ import annotations

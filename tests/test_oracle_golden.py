@@ -1,7 +1,8 @@
 """The CPU oracle against the committed golden fixtures (tests/golden/, made by oracle/gen_golden.py).
 
-Parity is UNPINNED against the reference itself (its arithmetic lives in absent PyPI packages and its tests hold
-no vectors, see oracle/oracle.py); these fixtures pin the oracle + synthetic-weight recipe against drift.  The
+These fixtures are the oracle's own outputs: they pin the oracle + synthetic-weight recipe against drift (whole path:
+pre / tile / post-processing, every model family).  The reference-made vectors that pin the RRDBNet arithmetic to the
+reference's own code are tests/golden/reference_made/ (tests/test_reference_pin.py).  The
 oracle is fp32 torch on CPU: results are allowed to differ from the fixture by 1 LSB on <= 0.1 % of pixels
 (different oneDNN kernels / thread counts change the fp32 summation order).
 """
