@@ -476,13 +476,27 @@ def run_b200(args):
     del dev_in, dev_out
     torch.cuda.empty_cache()
     barrier()
+    sched_hung = False
     if rank == 0 and args.sched_frames > 0:
-        try:
-            from tools.clip_bench import run_clip_job
+        # the contract line must not depend on this leg: an exception becomes an `error` entry, and a leg that does not
+        # come back within --sched-timeout seconds is abandoned (the line is printed, then the process leaves hard)
+        import threading
 
-            line["product_scheduler"] = run_clip_job(world, args.sched_frames, batch=2, threads=3)
-        except Exception as e:  # the contract line must not depend on it
-            line["product_scheduler"] = {"error": f"{type(e).__name__}: {e}"}
+        box = {}
+
+        def leg():
+            try:
+                from tools.clip_bench import run_clip_job
+
+                box["res"] = run_clip_job(world, args.sched_frames, batch=2, threads=3)
+            except BaseException as e:
+                box["res"] = {"error": f"{type(e).__name__}: {e}"}
+
+        th = threading.Thread(target=leg, name="product-scheduler-leg", daemon=True)
+        th.start()
+        th.join(timeout=args.sched_timeout)
+        sched_hung = th.is_alive()
+        line["product_scheduler"] = {"error": f"no result within {args.sched_timeout} s"} if sched_hung else box["res"]
     if world > 1:
         # host-side rendezvous (an NCCL barrier would park a spinning kernel on the GPUs the scheduler is using)
         from datetime import timedelta
@@ -495,7 +509,9 @@ def run_b200(args):
         else:
             store.wait(["b200sr_sched_done"], timedelta(seconds=900))
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    if sched_hung:
+        os._exit(0)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -515,6 +531,7 @@ def main():
     ap.add_argument("--sched-frames", type=int, default=-1,
                     help="frames of the clip pushed through the product scheduler after the main measurement "
                          "(default: 96 per GPU; 0 = skip)")
+    ap.add_argument("--sched-timeout", type=float, default=420.0, help="seconds the product-scheduler leg may take")
     ap.add_argument("--clip-batch", type=int, default=2, help="frames per engine call in the scheduler's workers")
     ap.add_argument("--clip-threads", type=int, default=3, help="runner threads per worker process")
     ap.add_argument("--no-cpu-baseline", action="store_true")
