@@ -292,3 +292,47 @@ def test_engine_workspace_formula_matches_the_c_abi(native_lib):
     free_mb = torch.cuda.mem_get_info(0)[0] >> 20
     assert calculate_optimal_tile_size((1280, 720), 4, available_vram_mb=free_mb) == 0      # a 720p frame fits whole
     assert calculate_optimal_tile_size((1280, 720), 4, available_vram_mb=2000) >= 128
+
+
+def test_plugin_adapters_on_the_device(native_lib, weights_dir, tmp_path):
+    """The adapters behind the reference's optional operator interfaces (plugin_adapters.py) with the REAL engine:
+    frame processor (batched runs of same-size frames == single calls, gate vs the oracle), a session that owns a
+    checkpoint named by path, and the video processor (cv2 file in -> upscaled cv2 file out)."""
+    import cv2
+
+    from framewright_b200 import plugin_adapters as pa
+    from framewright_b200 import pytorch_realesrgan as pr
+    from oracle import oracle
+
+    name = "RealESRGAN_x4plus_anime_6B"
+    frames = [oracle.synthetic_frame(40, 56, seed=60 + i, kind="mixed") for i in range(5)]
+    frames.append(oracle.synthetic_frame(32, 48, seed=70, kind="noise"))
+    proc = pa.B200FrameProcessor(device="cuda:0", model_name=name, max_batch=4)
+    got = proc.process_frames(frames)
+    up = pr.get_upsampler(pr.PyTorchESRGANConfig(model_name=name, gpu_id=0))
+    for f, g in zip(frames, got):
+        assert np.array_equal(g, up.enhance(f)[0])
+    _gate(_oracle(name, frames[0]), got[0], "B200FrameProcessor")
+    assert np.array_equal(proc.process_frame(frames[5]), got[5])
+    own = pa.UpscaleSession("cuda:0", {"model_name": name}, model_path=weights_dir / f"{name}.pth")
+    assert own.open() is not up and np.array_equal(own.frame(frames[1]), got[1])
+    own.close()
+    src, dst = tmp_path / "in.avi", tmp_path / "out.avi"
+    w = cv2.VideoWriter(str(src), cv2.VideoWriter_fourcc(*"MJPG"), 25.0, (56, 40))
+    assert w.isOpened()
+    for f in frames[:5]:
+        w.write(f)
+    w.release()
+    prog = []
+    vp = pa.B200VideoProcessor(device="cuda:0", fourcc="MJPG", model_name=name, max_batch=2)
+    assert vp.process_video(src, dst, progress_callback=prog.append) is True
+    assert vp.frames_processed == 5 and prog[-1] == 1.0
+    cap = cv2.VideoCapture(str(dst))
+    assert (int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))) == (224, 160)
+    n = 0
+    while cap.read()[0]:
+        n += 1
+    cap.release()
+    assert n == 5
+    assert proc.process_frame(frames[0], scale=2).shape == (80, 112, 3)     # outscale != net scale: resized result
+    proc.close()

@@ -113,6 +113,28 @@ def _device_bytes_in_use(gpu_id: int) -> int:
         return 0
 
 
+def upscale_frame_list(up: Any, frames: List[np.ndarray], scale: float = 4, max_batch: int = 16) -> List[np.ndarray]:
+    """A list of frames through one upsampler: runs of same-size BGR uint8 frames as ONE engine call each (at most
+    `max_batch` frames), anything else (gray, alpha, 16-bit, an `outscale` that is not the network's) frame by frame."""
+    out: List[Optional[np.ndarray]] = [None] * len(frames)
+    i = 0
+    while i < len(frames):
+        f = frames[i]
+        plain = isinstance(f, np.ndarray) and f.ndim == 3 and f.shape[2] == 3 and f.dtype == np.uint8
+        j = i + 1
+        if plain and float(scale) == float(up.scale):
+            while j < len(frames) and j - i < max_batch and isinstance(frames[j], np.ndarray) \
+                    and frames[j].shape == f.shape and frames[j].dtype == np.uint8:
+                j += 1
+            res = up.enhance_batch(np.stack(frames[i:j]))
+            for k in range(i, j):
+                out[k] = res[k - i]
+        else:
+            out[i] = up.enhance(f, outscale=scale)[0]
+        i = j
+    return out  # type: ignore[return-value]
+
+
 class B200RealESRGANBackend(SRBackend):
     """The reference's `RealESRGANBackend` contract on the B200 engine."""
 
@@ -179,24 +201,7 @@ class B200RealESRGANBackend(SRBackend):
     def process(self, frames: List[np.ndarray], scale: int = 4) -> List[np.ndarray]:
         """List of frames in, list of frames out (`SuperResolution.process`, :1502-1519): runs of same-size BGR uint8
         frames go through `upscale_array`, anything else (gray, alpha, 16-bit) through `upscale_frame`."""
-        up = get_upsampler(self._ensure_config())
-        out: List[Optional[np.ndarray]] = [None] * len(frames)
-        i = 0
-        while i < len(frames):
-            f = frames[i]
-            plain = isinstance(f, np.ndarray) and f.ndim == 3 and f.shape[2] == 3 and f.dtype == np.uint8
-            j = i + 1
-            if plain and float(scale) == float(up.scale):
-                while j < len(frames) and j - i < 16 and isinstance(frames[j], np.ndarray) \
-                        and frames[j].shape == f.shape and frames[j].dtype == np.uint8:
-                    j += 1
-                res = up.enhance_batch(np.stack(frames[i:j]))
-                for k in range(i, j):
-                    out[k] = res[k - i]
-            else:
-                out[i] = up.enhance(f, outscale=scale)[0]
-            i = j
-        return out  # type: ignore[return-value]
+        return upscale_frame_list(get_upsampler(self._ensure_config()), frames, scale)
 
     # ---- frames directory in, frames directory out
     def upscale_frames(self, input_dir: Path, output_dir: Path, scale: int = 4,
