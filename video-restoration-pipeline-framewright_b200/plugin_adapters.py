@@ -158,7 +158,7 @@ def make_processor_plugin(base_module: Any = None):
     """Returns `B200RealESRGANPlugin`, a subclass of the reference's `ProcessorPlugin` (`base_module` =
     `framewright.plugins.base`, imported if not given; the class is created once per base module)."""
     base = base_module or importlib.import_module("framewright.plugins.base")
-    cached = _PLUGIN_CLASSES.get(id(base))
+    cached = _PLUGIN_CLASSES.get(base)
     if cached is not None:
         return cached
 
@@ -216,11 +216,11 @@ def make_processor_plugin(base_module: Any = None):
         def get_progress_weight(self) -> float:
             return 10.0                   # the heavy stage of a restoration (17.9 M MAC per input pixel)
 
-    _PLUGIN_CLASSES[id(base)] = B200RealESRGANPlugin
+    _PLUGIN_CLASSES[base] = B200RealESRGANPlugin
     return B200RealESRGANPlugin
 
 
-_PLUGIN_CLASSES: Dict[int, Any] = {}
+_PLUGIN_CLASSES: Dict[Any, Any] = {}      # base module -> class (one class per set of base classes)
 
 
 def register_plugin(manager_or_registry: Any, base_module: Any = None):
@@ -236,8 +236,8 @@ def register_plugin(manager_or_registry: Any, base_module: Any = None):
 # ---------------------------------------------------------------------------------------------------------------------
 class B200FrameProcessor:
     """`PipelineStage(name="upscale", processor=B200FrameProcessor(model_name=..., device="cuda:0"))`: satisfies the
-    reference's `FrameProcessor` protocol; per-call keyword arguments override the settings for that call's frames
-    (they are the stage's `StageConfig.params`)."""
+    reference's `FrameProcessor` protocol.  Keyword arguments are the stage's `StageConfig.params` (the same for every
+    frame of a stage): known ones update the settings and stay in force.  One caller thread at a time per object."""
 
     def __init__(self, device: Any = "cuda:0", **settings: Any):
         self._session = UpscaleSession(device, settings)
@@ -396,7 +396,7 @@ def make_compute_backend(base_module: Any = None, detector_module: Any = None):
     frames)` runs it on a BGR uint8 frame, a frame stack [N,H,W,3] or a list of frames."""
     base = base_module or importlib.import_module("framewright.infrastructure.gpu.backends.base")
     det = detector_module or importlib.import_module("framewright.infrastructure.gpu.detector")
-    cached = _BACKEND_CLASSES.get(id(base))
+    cached = _BACKEND_CLASSES.get(base)
     if cached is not None:
         return cached
 
@@ -503,11 +503,11 @@ def make_compute_backend(base_module: Any = None, detector_module: Any = None):
                 return session.frames(inputs)
             return session.frame(inputs)
 
-    _BACKEND_CLASSES[id(base)] = B200Backend
+    _BACKEND_CLASSES[base] = B200Backend
     return B200Backend
 
 
-_BACKEND_CLASSES: Dict[int, Any] = {}
+_BACKEND_CLASSES: Dict[Any, Any] = {}
 
 
 def register_compute_backend(base_module: Any = None, detector_module: Any = None):
