@@ -198,3 +198,78 @@ def test_raw_video_pipes_round_trip():
     out = np.frombuffer(dst.getvalue(), np.uint8).reshape(n, 2 * h, 2 * w, 3)
     assert np.array_equal(out, np.repeat(np.repeat(clip, 2, axis=1), 2, axis=2))
     assert len(list(RawVideoReader(io.BytesIO(clip.tobytes()), w, h))) == n
+
+
+_FAKE_FFMPEG = '''#!/usr/bin/env python3
+"""Stand-in for ffmpeg in the pipe test: `-i <file> ... pipe:1` writes the file's bytes to stdout (decoder);
+`-i pipe:0 ... -y <out>` copies stdin to <out> and records its argv next to it (encoder)."""
+import json, os, sys
+a = sys.argv[1:]
+src = a[a.index("-i") + 1]
+if src == "pipe:0":
+    out = a[-1]
+    if os.environ.get("FAKE_FFMPEG_ENCODER_DIES"):
+        sys.stdin.buffer.read(1000)
+        sys.stderr.write("Unknown encoder 'libx265'\\n")
+        sys.exit(1)
+    with open(out, "wb") as f:
+        while True:
+            b = sys.stdin.buffer.read(1 << 16)
+            if not b:
+                break
+            f.write(b)
+    json.dump(a, open(out + ".argv.json", "w"))
+else:
+    if not os.path.exists(src):
+        sys.stderr.write(src + ": No such file or directory\\n")
+        sys.exit(1)
+    sys.stdout.buffer.write(open(src, "rb").read())
+'''
+
+
+def test_video_file_through_ffmpeg_pipes(tmp_path, monkeypatch):
+    """f1 end to end: decoder process -> raw frames -> engine -> raw frames -> encoder process, no frame files; the
+    encoder gets the reference's codec arguments (restorer.py:3001-3027) and the SCALED frame size; a failing ffmpeg on
+    either side is an `EnhancementError` carrying its stderr, not a hang."""
+    import json
+    import stat
+
+    from framewright_b200.pytorch_realesrgan import PyTorchESRGANConfig
+    from framewright_b200.restorer_adapter import (EnhancementError, ffmpeg_decode_command, ffmpeg_encode_command,
+                                                   upscale_video_ffmpeg)
+
+    exe = tmp_path / "ffmpeg"
+    exe.write_text(_FAKE_FFMPEG)
+    exe.chmod(exe.stat().st_mode | stat.S_IEXEC)
+    h, w, n = 6, 10, 9
+    clip = np.random.default_rng(1).integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
+    src, dst, audio = tmp_path / "in.raw", tmp_path / "out.bin", tmp_path / "audio.flac"
+    src.write_bytes(clip.tobytes())
+    audio.write_bytes(b"x")
+    cfg = PyTorchESRGANConfig(model_name="RealESRGAN_x2plus", scale_factor=2)
+    prog = []
+    written = upscale_video_ffmpeg(src, dst, cfg, width=w, height=h, framerate=24, num_frames=n, audio_path=audio,
+                                   crf=16, preset="slow", ffmpeg=str(exe), batch=4,
+                                   upsampler=fake_engine({"gpu_id": 1}), progress_callback=lambda f, m: prog.append(f))
+    assert written == n and prog[-1] == 1.0
+    out = np.frombuffer(dst.read_bytes(), np.uint8).reshape(n, 2 * h, 2 * w, 3)
+    assert np.array_equal(out, np.repeat(np.repeat(clip, 2, axis=1), 2, axis=2))
+    argv = json.load(open(str(dst) + ".argv.json"))
+    assert argv[argv.index("-s") + 1] == f"{2 * w}x{2 * h}" and argv[argv.index("-framerate") + 1] == "24"
+    assert argv[argv.index("-c:v") + 1] == "libx265" and argv[argv.index("-crf") + 1] == "16"
+    assert argv[argv.index("-preset") + 1] == "slow" and argv[argv.index("-pix_fmt", argv.index("-c:v")) + 1] == "yuv420p10le"
+    assert argv[argv.index("-c:a") + 1] == "flac" and str(audio) in argv and argv[-2:] == ["-y", str(dst)]
+    assert ffmpeg_decode_command("a.mp4")[-5:] == ["-f", "rawvideo", "-pix_fmt", "bgr24", "pipe:1"]
+    assert "-c:a" not in ffmpeg_encode_command("o.mp4", 8, 8, 30)                       # no audio track given
+    with pytest.raises(EnhancementError, match="decoder failed.*No such file"):
+        upscale_video_ffmpeg(tmp_path / "missing.raw", dst, cfg, width=w, height=h, ffmpeg=str(exe),
+                             upsampler=fake_engine({"gpu_id": 1}))
+    monkeypatch.setenv("FAKE_FFMPEG_ENCODER_DIES", "1")
+    big = np.zeros((40, 64, 64, 3), np.uint8)                      # enough bytes to fill the pipe of a dead encoder
+    (tmp_path / "big.raw").write_bytes(big.tobytes())
+    with pytest.raises(EnhancementError, match="encoder failed.*Unknown encoder"):
+        upscale_video_ffmpeg(tmp_path / "big.raw", dst, cfg, width=64, height=64, ffmpeg=str(exe),
+                             upsampler=fake_engine({"gpu_id": 1}))
+    with pytest.raises(EnhancementError, match="cannot start the decoder"):
+        upscale_video_ffmpeg(src, dst, cfg, width=w, height=h, ffmpeg=str(tmp_path / "no-such-ffmpeg"),
+                             upsampler=fake_engine({"gpu_id": 1}))

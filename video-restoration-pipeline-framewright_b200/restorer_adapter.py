@@ -14,7 +14,8 @@ f4  `make_streaming_enhancer` -> the `enhance_fn(List[PipelineFrame]) -> List[Pi
     scheduler's worker processes and shared-memory transport.
 f1  `RawVideoReader` / `RawVideoWriter`: raw bgr24 frame pipes (what `ffmpeg -f rawvideo -pix_fmt bgr24 -` produces /
     consumes) and `upscale_raw_stream`, the decode -> engine -> encode path with no PNG round trip and no per-frame
-    `ffprobe` (`restorer.py:1109-1118, 3001-3027`, `validators.py:165-181`).
+    `ffprobe` (`restorer.py:1109-1118, 3001-3027`, `validators.py:165-181`); `upscale_video_ffmpeg` runs it between
+    an ffmpeg decoder and an ffmpeg encoder process (the reference's own codec arguments).
 """
 from __future__ import annotations
 
@@ -425,3 +426,81 @@ def upscale_raw_stream(src: BinaryIO, dst: BinaryIO, width: int, height: int, co
             flush()
     flush()
     return writer.frames
+
+
+def ffmpeg_decode_command(video_path: Any, ffmpeg: str = "ffmpeg") -> List[str]:
+    """The decoder side of `VideoRestorer.extract_frames` (`restorer.py:1109-1118`) with the PNG sequence replaced by
+    raw bgr24 frames on stdout."""
+    return [ffmpeg, "-v", "error", "-i", str(video_path), "-f", "rawvideo", "-pix_fmt", "bgr24", "pipe:1"]
+
+
+def ffmpeg_encode_command(output_path: Any, width: int, height: int, framerate: Any, audio_path: Any = None,
+                          codec: str = "libx265", pix_fmt: str = "yuv420p10le", crf: int = 18, preset: str = "medium",
+                          ffmpeg: str = "ffmpeg") -> List[str]:
+    """The encoder side of `VideoRestorer.reassemble_video` (`restorer.py:3001-3027`: `-framerate`, optional audio as
+    FLAC, `-c:v <codec> -crf <crf> -preset <preset> -pix_fmt <fmt> -y out`) with the PNG sequence replaced by raw
+    bgr24 frames of `width` x `height` on stdin."""
+    cmd = [ffmpeg, "-v", "error", "-f", "rawvideo", "-pix_fmt", "bgr24", "-s", f"{int(width)}x{int(height)}",
+           "-framerate", str(framerate), "-i", "pipe:0"]
+    if audio_path is not None and Path(audio_path).exists():
+        cmd += ["-i", str(audio_path), "-c:a", "flac"]
+    cmd += ["-c:v", codec, "-crf", str(crf), "-preset", preset, "-pix_fmt", pix_fmt, "-y", str(output_path)]
+    return cmd
+
+
+def upscale_video_ffmpeg(video_path: Any, output_path: Any, config: PyTorchESRGANConfig, *, width: int, height: int,
+                         framerate: Any = 30, num_frames: Optional[int] = None, audio_path: Any = None,
+                         codec: str = "libx265", pix_fmt: str = "yuv420p10le", crf: int = 18, preset: str = "medium",
+                         ffmpeg: str = "ffmpeg", pool: Any = None, batch: int = 4, upsampler: Any = None,
+                         progress_callback: Optional[Callable[[float, str], None]] = None) -> int:
+    """video file -> ffmpeg decoder -> raw frames -> engine(s) -> raw frames -> ffmpeg encoder -> video file: the
+    reference's extract_frames / enhance_frames / reassemble_video sequence (`restorer.py:1076-1160, 1604-1705,
+    2950-3060`) as ONE pass with no frame files in between.  `width`, `height`, `framerate` (and `num_frames`, which lets
+    a `SchedulerPool` spread the frames over its GPUs) are what the reference reads into `self.metadata` with ffprobe
+    before it starts.  Returns the number of frames written; raises `EnhancementError` when either ffmpeg fails."""
+    import subprocess
+    import tempfile
+
+    s = int(config.scale_factor)
+    dec_cmd = ffmpeg_decode_command(video_path, ffmpeg)
+    enc_cmd = ffmpeg_encode_command(output_path, width * s, height * s, framerate, audio_path, codec, pix_fmt, crf,
+                                    preset, ffmpeg)
+    # stderr goes to files: nobody reads those pipes while the frames flow, and a full pipe would stall ffmpeg
+    with tempfile.TemporaryFile() as dec_err, tempfile.TemporaryFile() as enc_err:
+        try:
+            dec = subprocess.Popen(dec_cmd, stdout=subprocess.PIPE, stderr=dec_err, stdin=subprocess.DEVNULL)
+        except OSError as e:
+            raise EnhancementError(f"cannot start the decoder ({dec_cmd[0]}): {e}") from e
+        try:
+            enc = subprocess.Popen(enc_cmd, stdin=subprocess.PIPE, stderr=enc_err, stdout=subprocess.DEVNULL)
+        except OSError as e:
+            dec.kill()
+            dec.wait()
+            raise EnhancementError(f"cannot start the encoder ({enc_cmd[0]}): {e}") from e
+        written, failure = 0, None
+        try:
+            written = upscale_raw_stream(dec.stdout, enc.stdin, width, height, config, num_frames=num_frames, pool=pool,
+                                         batch=batch, upsampler=upsampler, progress_callback=progress_callback)
+        except BrokenPipeError as e:        # the encoder went away: its exit code and stderr say why
+            failure = e
+        except BaseException:
+            for p in (dec, enc):
+                p.kill()
+            raise
+        finally:
+            for stream in (enc.stdin, dec.stdout):
+                try:
+                    stream.close()
+                except Exception:
+                    pass
+            dec_rc, enc_rc = dec.wait(), enc.wait()
+
+        def tail(f) -> str:
+            f.seek(0)
+            return f.read()[-800:].decode("utf-8", "replace").strip()
+
+        if enc_rc != 0 or failure is not None:
+            raise EnhancementError(f"encoder failed (exit code {enc_rc}) after {written} frames: {tail(enc_err)}")
+        if dec_rc != 0:
+            raise EnhancementError(f"decoder failed (exit code {dec_rc}) after {written} frames: {tail(dec_err)}")
+    return written
