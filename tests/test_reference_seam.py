@@ -446,3 +446,154 @@ def test_reference_multi_gpu_processor_calls_the_b200_process_func(monkeypatch):
     assert [r.device_id for r in results] == [i % 2 for i in range(n)] and sorted(made) == [0, 1]
     assert all(r.success and r.output.shape == (8, 12, 3) and int(r.output[0, 0, 0]) == r.frame_index for r in results[:-1])
     assert results[-1].success is False and results[-1].error and stats.errors == 1
+
+
+# ---- the remaining call sites of the upsampler duck type, their source text unmodified ------
+def _reference_function(path, name):
+    """Source of one module-level function of a reference file, verbatim."""
+    import ast
+
+    src = open(path).read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            return "\n".join(src.splitlines()[node.lineno - 1:node.end_lineno])
+    raise AssertionError(f"{name} not found in {path}")
+
+
+@pytest.fixture()
+def shimmed_oracle_engine(monkeypatch, tmp_path):
+    """`from realesrgan import RealESRGANer` / `from basicsr.archs.rrdbnet_arch import RRDBNet` resolve to the shims;
+    the engine behind them is the CPU oracle (no GPU here); synthetic checkpoints under the names upstream ships."""
+    import torch
+
+    import framewright_b200  # noqa: F401
+    from framewright_b200 import shims
+    from framewright_b200 import upsampler as up_mod
+    from framewright_b200.archs import make_synthetic_state_dict
+    from oracle import oracle
+
+    calls = []
+
+    class OracleEngine:
+        def __init__(self, arch, state_dict, gpu_id=0):
+            self.name = next(k for k, v in up_mod.MODEL_ARCHS.items() if v == arch)
+            self.sd = state_dict
+
+        def upscale_host(self, frames, out=None, tile=0, tile_pad=10, pre_pad=0):
+            calls.append((self.name, tile, tile_pad, pre_pad))
+            return oracle.make_upsampler(self.name, self.sd, tile=tile, tile_pad=tile_pad, pre_pad=pre_pad).enhance(frames)[0]
+
+        def close(self):
+            pass
+
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("realesrgan", "basicsr")}
+    monkeypatch.setattr(up_mod, "B200Engine", OracleEngine)
+    shims.install()
+    models = tmp_path / "home" / ".framewright" / "models"
+    models.mkdir(parents=True)
+    for name in ("RealESRGAN_x4plus_anime_6B", "realesr-animevideov3"):
+        torch.save({"params_ema": make_synthetic_state_dict(name, 0)}, str(models / f"{name}.pth"))
+    # (a 6-block stand-in under the x4plus FILE name keeps the CPU oracle fast: the architecture comes from the
+    #  RRDBNet(...) object the caller passes, which is exactly what is being tested)
+    yield calls, models
+    for k in [k for k in sys.modules if k.split(".")[0] in ("realesrgan", "basicsr")]:
+        del sys.modules[k]
+    sys.modules.update(saved)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_reference_cli_enhance_frames_runs_verbatim_over_the_shims(shimmed_oracle_engine, tmp_path, monkeypatch, capsys):
+    """`framewright enhance-frames` (`cli.py:699-775`, `_enhance_with_realesrgan`, source unmodified): RRDBNet(...) object +
+    `RealESRGANer(scale, model_path, model, tile=512, tile_pad=10, pre_pad=10, half=True)` + `enhance(img, outscale)` per
+    frame file.  The 'anime' branch names realesr-animevideov3.pth and passes a 6-block RRDBNet: the checkpoint's name
+    selects the SRVGG network upstream ships under it (SURVEY finding 3)."""
+    import types
+
+    import cv2
+    import tqdm
+
+    from framewright_b200.archs import make_synthetic_state_dict
+    from oracle import oracle
+
+    calls, models = shimmed_oracle_engine
+    monkeypatch.setenv("HOME", str(tmp_path / "home"))
+    ns = {"Path": Path, "sys": sys, "tqdm": tqdm.tqdm,
+          "print_colored": lambda msg, color=None: print(msg),
+          "Colors": types.SimpleNamespace(OKCYAN="", WARNING="", FAIL="", OKGREEN="", OKBLUE="")}
+    exec(_reference_function(os.path.join(REF, "cli.py"), "_enhance_with_realesrgan"), ns)
+    ind, outd = tmp_path / "frames", tmp_path / "enhanced"
+    ind.mkdir()
+    outd.mkdir()
+    frames = []
+    for i in range(3):
+        img = oracle.synthetic_frame(18, 22, seed=80 + i, kind="mixed")
+        cv2.imwrite(str(ind / f"frame_{i + 1:08d}.png"), img)
+        frames.append(img)
+    (ind / "frame_00000004.png").write_bytes(b"not a png")                     # unreadable: counted as failed, no raise
+    files = sorted(ind.glob("*.png"))
+    ns["_enhance_with_realesrgan"](types.SimpleNamespace(model="realesr-animevideov3-anime"), ind, outd, 4, files)
+    assert calls and set(calls) == {("realesr-animevideov3", 512, 10, 10)}
+    want_up = oracle.make_upsampler("realesr-animevideov3", make_synthetic_state_dict("realesr-animevideov3", 0),
+                                    tile=512, tile_pad=10, pre_pad=10)
+    for i, img in enumerate(frames):
+        got = cv2.imread(str(outd / f"frame_{i + 1:08d}.png"), cv2.IMREAD_UNCHANGED)
+        assert np.array_equal(got, want_up.enhance(img)[0])
+    out = capsys.readouterr().out
+    assert "Enhanced 3/4 frames" in out and "1 frames failed" in out
+    # no checkpoint of the requested model and no fallback file: the reference prints and exits 1 -- never random weights
+    for f in models.glob("*.pth"):
+        f.unlink()
+    with pytest.raises(SystemExit):
+        ns["_enhance_with_realesrgan"](types.SimpleNamespace(model="realesrgan-x4plus"), ind, outd, 4, files)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_reference_gfpgan_background_upsampler_runs_verbatim_over_the_shims(shimmed_oracle_engine, tmp_path, monkeypatch):
+    """`FaceRestorer._get_bg_upsampler` (`processors/face_restore.py:379-401`, source unmodified): RRDBNet(23 blocks) object
+    + `RealESRGANer(scale=4, model_path='RealESRGAN_x4plus.pth', model=model, tile=400, tile_pad=10, pre_pad=0, half=True)`
+    -- a BARE file name, resolved in the weights directory."""
+    import shutil
+    import types
+
+    from framewright_b200.archs import make_synthetic_state_dict
+    from oracle import oracle
+
+    calls, models = shimmed_oracle_engine
+    ns = {}
+    exec(_reference_method(os.path.join(REF, "processors/face_restore.py"), "FaceRestorer", "_get_bg_upsampler"), ns)
+    me = types.SimpleNamespace(bg_upsampler="realesrgan")
+    monkeypatch.setenv("B200SR_WEIGHTS_DIR", str(tmp_path / "empty"))
+    assert ns["_get_bg_upsampler"](me) is None               # no such checkpoint: the reference swallows it -> no upsampler
+    assert ns["_get_bg_upsampler"](types.SimpleNamespace(bg_upsampler="none")) is None
+    import torch
+
+    wdir = tmp_path / "weights"
+    wdir.mkdir()
+    torch.save({"params": make_synthetic_state_dict("RealESRGAN_x4plus", 0)}, str(wdir / "RealESRGAN_x4plus.pth"))
+    monkeypatch.setenv("B200SR_WEIGHTS_DIR", str(wdir))
+    up = ns["_get_bg_upsampler"](me)
+    assert up is not None and (up.scale, up.tile_size, up.tile_pad, up.pre_pad) == (4, 400, 10, 0)
+    img = oracle.synthetic_frame(12, 14, seed=9, kind="mixed")
+    out, mode = up.enhance(img, outscale=2)                  # GFPGAN asks for its own upscale factor: resized result
+    assert mode == "RGB" and out.shape == (24, 28, 3) and calls[-1] == ("RealESRGAN_x4plus", 400, 10, 0)
+    up.close()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_reference_dependency_check_finds_the_shims(shimmed_oracle_engine, monkeypatch):
+    """`utils/dependencies.py::check_realesrgan` (:263-345, the module loaded unmodified): with no ncnn binary on the
+    machine it verifies `import torch; from realesrgan import RealESRGANer; from basicsr.archs.rrdbnet_arch import
+    RRDBNet` and reads `realesrgan.__version__` -- which is what lets `VideoRestorer.__init__` pass
+    `_verify_dependencies` (restorer.py:393-406)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_ref_dependencies", os.path.join(REF, "utils", "dependencies.py"))
+    dep = importlib.util.module_from_spec(spec)
+    monkeypatch.setitem(sys.modules, "_ref_dependencies", dep)
+    monkeypatch.setattr(sys, "dont_write_bytecode", True)
+    spec.loader.exec_module(dep)
+    monkeypatch.setattr(dep.shutil, "which", lambda cmd: None)
+    monkeypatch.setattr(dep.Path, "home", classmethod(lambda cls: Path("/nonexistent-home")))
+    info = dep.check_realesrgan()
+    assert info.installed is True and info.additional_info["backend"] == "pytorch"
+    assert info.version.endswith("+b200sr") and info.path == "realesrgan (Python package)"
