@@ -597,3 +597,127 @@ def test_reference_dependency_check_finds_the_shims(shimmed_oracle_engine, monke
     info = dep.check_realesrgan()
     assert info.installed is True and info.additional_info["backend"] == "pytorch"
     assert info.version.endswith("+b200sr") and info.path == "realesrgan (Python package)"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_video_restorer_thread_parallel_caller_runs_verbatim_against_the_mirror(tmp_path, monkeypatch):
+    """SURVEY 8 a10 / (b) threading: `VideoRestorer._enhance_frames_parallel` (restorer.py:1823-1973), `_enhance_single_frame`
+    (:1386-1418) and `_enhance_single_frame_pytorch` (:1420-1460) -- source text unmodified -- drive the mirror's
+    `enhance_frame_pytorch` from `parallel_frames` = 4 threads: every frame written and checkpointed, progress to 1.0;
+    an out-of-memory answer walks the caller's tile ladder ("memory" in the message, :1746 / :1878) and the frames
+    still complete on the smaller tile."""
+    import shutil
+    import threading
+    import time
+    import types
+    from concurrent.futures import ThreadPoolExecutor, as_completed
+    from typing import List, Optional, Tuple
+
+    import cv2
+    import torch
+
+    from framewright_b200 import pytorch_realesrgan as mine
+    from framewright_b200 import upsampler as up_mod
+    from framewright_b200.archs import make_synthetic_state_dict
+    from framewright_b200.engine import EngineOutOfMemory
+    from framewright_b200.restorer_adapter import EnhancementError, validate_frame_integrity
+    from oracle import oracle
+
+    name = "RealESRGAN_x4plus_anime_6B"
+    state = {"oom_above_tile": None, "threads": set(), "tiles": []}
+
+    class OracleEngine:
+        def __init__(self, arch, state_dict, gpu_id=0):
+            self.sd = state_dict
+
+        def upscale_host(self, frames, out=None, tile=0, tile_pad=10, pre_pad=0):
+            state["threads"].add(threading.get_ident())
+            lim = state["oom_above_tile"]
+            if lim is not None and (tile == 0 or tile > lim):
+                raise EngineOutOfMemory("GPU out of memory: out of memory allocating workspace")
+            state["tiles"].append((tile, hash(np.asarray(frames).tobytes())))
+            return oracle.make_upsampler(name, self.sd, tile=tile, tile_pad=tile_pad, pre_pad=pre_pad).enhance(frames)[0]
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(up_mod, "B200Engine", OracleEngine)
+    monkeypatch.setattr(mine, "is_pytorch_esrgan_available", lambda: True)
+    monkeypatch.setattr(mine, "_auto_tile", lambda gpu: 0)
+    monkeypatch.setattr(mine, "_available_vram_mb", lambda gpu: 50000.0)
+    wdir = tmp_path / "weights"
+    wdir.mkdir()
+    torch.save({"params_ema": make_synthetic_state_dict(name, 0)}, str(wdir / f"{name}.pth"))
+    monkeypatch.setenv("B200SR_WEIGHTS_DIR", str(wdir))
+    mine.clear_upsampler_cache()
+
+    class Report:
+        def __init__(self):
+            self.ok, self.errors = 0, []
+
+        def add_success(self):
+            self.ok += 1
+
+        def add_error(self, frame, exc):
+            self.errors.append((frame, str(exc)))
+
+    logger = types.SimpleNamespace(info=lambda *a, **k: None, warning=lambda *a, **k: None, error=lambda *a, **k: None,
+                                   debug=lambda *a, **k: None)
+    ns = {"Path": Path, "Tuple": Tuple, "Optional": Optional, "List": List, "ErrorReport": Report, "time": time,
+          "shutil": shutil, "logger": logger, "ThreadPoolExecutor": ThreadPoolExecutor, "as_completed": as_completed,
+          "EnhancementError": EnhancementError, "is_pytorch_esrgan_available": mine.is_pytorch_esrgan_available,
+          "convert_ncnn_model_name": mine.convert_ncnn_model_name, "PyTorchESRGANConfig": mine.PyTorchESRGANConfig,
+          "enhance_frame_pytorch": mine.enhance_frame_pytorch, "validate_frame_integrity": validate_frame_integrity}
+    for meth in ("_enhance_frames_parallel", "_enhance_single_frame", "_enhance_single_frame_pytorch"):
+        exec(_reference_method(os.path.join(REF, "restorer.py"), "VideoRestorer", meth), ns)
+
+    ind, outd = tmp_path / "frames", tmp_path / "enhanced"
+    ind.mkdir()
+    outd.mkdir()
+    imgs, frames = [], []
+    for i in range(8):
+        img = oracle.synthetic_frame(40, 44, seed=120 + i, kind="mixed")
+        p = ind / f"frame_{i + 1:08d}.png"
+        cv2.imwrite(str(p), img)
+        imgs.append(img)
+        frames.append(p)
+    checkpointed, progress = [], []
+    me = types.SimpleNamespace(
+        config=types.SimpleNamespace(parallel_frames=4, enhanced_dir=outd, max_retries=2, retry_delay=0.0,
+                                     continue_on_error=False, model_name="realesrgan-x4plus-anime", scale_factor=4,
+                                     gpu_id=None),
+        checkpoint_manager=types.SimpleNamespace(update_frame=lambda **k: checkpointed.append(k["frame_number"])),
+        _vram_monitor=None, _reset_stage_timing=lambda stage: None, _record_frame_time=lambda t: None,
+        _check_disk_space=lambda: None, _get_enhancement_backend=lambda: "pytorch",
+        _update_progress=lambda **k: progress.append(k["progress"]))
+    for meth in ("_enhance_single_frame", "_enhance_single_frame_pytorch"):
+        setattr(me, meth, types.MethodType(ns[meth], me))
+
+    rep = Report()
+    n = ns["_enhance_frames_parallel"](me, frames, 0, [32, 24, 16], rep)
+    assert n == 8 and rep.ok == 8 and not rep.errors and sorted(checkpointed) == list(range(1, 9))
+    assert progress[-1] == 1.0 and len(state["threads"]) > 1                     # really called from several threads
+    want_up = oracle.make_upsampler(name, make_synthetic_state_dict(name, 0), tile=0, pre_pad=0)
+    for i, img in enumerate(imgs):
+        assert np.array_equal(cv2.imread(str(outd / frames[i].name), cv2.IMREAD_UNCHANGED), want_up.enhance(img)[0])
+
+    # the device "fills up": nothing above a 24-pixel tile fits any more.  The caller starts from its configured tile
+    # and every failing thread steps the shared tile size down once (the reference's own logic, racy by design: the
+    # ladder may overshoot), so the frames end on SOME tile <= 24 -- each output must be the tiled result for the tile
+    # it was computed with.
+    shutil.rmtree(outd)
+    outd.mkdir()
+    state.update(oom_above_tile=24, tiles=[])
+    me.config.max_retries = 3
+    mine.clear_upsampler_cache()
+    rep = Report()
+    n = ns["_enhance_frames_parallel"](me, frames, 48, [40, 36, 32, 28, 24, 20, 16, 12, 8], rep)
+    assert n == 8 and rep.ok == 8 and not rep.errors
+    used = {h: t for t, h in state["tiles"]}
+    assert len(used) == 8 and all(0 < t <= 24 for t in used.values())
+    sd = make_synthetic_state_dict(name, 0)
+    for i, img in enumerate(imgs):
+        t = used[hash(img.tobytes())]
+        want = oracle.make_upsampler(name, sd, tile=t, tile_pad=10, pre_pad=0).enhance(img)[0]
+        assert np.array_equal(cv2.imread(str(outd / frames[i].name), cv2.IMREAD_UNCHANGED), want), (i, t)
+    mine.clear_upsampler_cache()
