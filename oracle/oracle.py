@@ -3,7 +3,8 @@
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` leg may
 import this module; the product package never does (and fails loudly without its CUDA library).
 
-PARITY: the RRDBNet NETWORK is PINNED to reference-made vectors; `RealESRGANer` pre / tile / post-processing
+PARITY: the RRDBNet NETWORK (and the frame conventions around it: channel order, / 255, layout, clip) is PINNED to
+reference-made vectors; `RealESRGANer`'s final `round`, pre_pad / mod-pad, tile loop, gray / alpha / 16-bit branches
 and `SRVGGNetCompact` are UNPINNED.  The reference (`/root/reference/src/framewright/processors/pytorch_realesrgan.py`)
 does not contain the arithmetic of this path: it constructs and calls two third-party PyPI
 packages -- `basicsr` (class `RRDBNet`; last release 1.4.2) and `realesrgan` (classes `RealESRGANer`,
@@ -27,6 +28,8 @@ attention gate is the identity at the constructed gamma = 0).  `oracle/ref_pin.p
 loads the same checkpoints into it and commits what it computes (`tests/golden/reference_made/*.npz`);
 `tests/test_reference_pin.py` holds `RRDBNet` below to those vectors (x4plus, anime_6B, the x2plus network incl.
 `pixel_unshuffle` against torch's own) -- in this container bit for bit against the module run live.
+The same file's frame path around the network (`AESRGANFaceRestorer._enhance_face`, :516-542: BGR <-> RGB, / 255,
+layout, clip, x 255) pins those conventions of `enhance` too, up to the last step (it truncates, upstream rounds).
 The other committed fixtures, tests/golden/*.npz, are outputs of THIS oracle (generator:
 oracle/gen_golden.py), i.e. regression vectors, not reference-made vectors.
 """

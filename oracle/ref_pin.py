@@ -17,12 +17,17 @@ reference's own lines.  This script imports that file UNMODIFIED from /root/refe
 torch), loads the repo's synthetic checkpoints into it (RRDB k of the checkpoint -> the k-th RRDB of `body`, which
 is what the index shift of the inserted gate amounts to), runs it on seeded frames and commits input + output as
 
-    tests/golden/reference_made/*.npz      (frame uint8 BGR, `net_out` float32 (3, 4h', 4w') as the reference computed it)
+    tests/golden/reference_made/*.npz      (frame uint8 BGR; `net_out` float32 (3, 4h', 4w') as the reference computed
+                                            it; `frame_out_truncated` uint8 BGR: the same frame through the reference's
+                                            own pre- / post-processing around the network, `_enhance_face` :516-542)
 
 Covered: RealESRGAN_x4plus (23 blocks), RealESRGAN_x4plus_anime_6B (6 blocks) and the network of RealESRGAN_x2plus
 after its pixel-unshuffle (12 input channels; the unshuffle here is torch's own `F.pixel_unshuffle`, so the oracle's
-restated one is checked against an independent implementation too).  NOT covered by any reference code, hence
-still "unpinned": `RealESRGANer`'s pre / tile / post-processing and `SRVGGNetCompact`.
+restated one is checked against an independent implementation too).  The reference's own frame path around the
+network (`AESRGANFaceRestorer._enhance_face`: BGR <-> RGB, / 255, layout, clip, x 255) pins those conventions of
+`RealESRGANer.enhance` as well, up to its final rounding (the reference truncates, upstream rounds).  NOT covered by
+any reference code, hence still "unpinned": upstream's `round`, `pre_pad` / mod-pad, the tile loop, the 16-bit / gray /
+alpha branches, and `SRVGGNetCompact`.
 
     python oracle/ref_pin.py          # rewrites tests/golden/reference_made/ (needs /root/reference)
 """
@@ -102,7 +107,22 @@ def quantise(net_out: np.ndarray) -> np.ndarray:
     return (o * 255.0).round().astype(np.uint8)
 
 
+def reference_frame_path(mod, net, img_bgr_u8: np.ndarray) -> np.ndarray:
+    """uint8 BGR frame in -> uint8 BGR frame out through the reference's OWN pre- and post-processing around that
+    network: `AESRGANFaceRestorer._enhance_face` (`aesrgan_face.py:516-542`, the method itself, unmodified) -- BGR ->
+    RGB, `/ 255.0`, HWC -> NCHW, the model, NCHW -> HWC, `np.clip(x * 255.0, 0, 255).astype(np.uint8)`, RGB -> BGR.
+    Same conventions as `RealESRGANer.enhance` except the last step: the reference TRUNCATES where upstream ROUNDS
+    (`(x * 255.0).round()`), so upstream's result is this one, or this one + 1 where the fraction is >= 0.5."""
+    import types
+
+    import torch
+
+    me = types.SimpleNamespace(_model=net, _device=torch.device("cpu"), config=types.SimpleNamespace(half_precision=False))
+    return mod.AESRGANFaceRestorer._enhance_face(me, img_bgr_u8)
+
+
 def run_case(mod, c):
+    """-> (frame, the reference network's float output, the reference frame path's uint8 output or None)."""
     import torch
 
     sys.path.insert(0, ROOT)
@@ -115,7 +135,8 @@ def run_case(mod, c):
     img = oracle.synthetic_frame(h, w, seed=seed, kind=kind)
     with torch.no_grad():
         out = net(network_input(img, cin))
-    return img, out.squeeze(0).numpy().astype(np.float32)
+    frame_out = reference_frame_path(mod, net, img) if cin == 3 else None     # (no pixel-unshuffle in that path)
+    return img, out.squeeze(0).numpy().astype(np.float32), frame_out
 
 
 def main():
@@ -125,9 +146,10 @@ def main():
     mod = load_reference_module()
     os.makedirs(OUT_DIR, exist_ok=True)
     for c in CASES:
-        img, out = run_case(mod, c)
+        img, out, frame_out = run_case(mod, c)
         path = os.path.join(OUT_DIR, case_name(c) + ".npz")
-        np.savez_compressed(path, input=img, net_out=out, meta=np.array(c[1:5] + c[6:7]))
+        extra = {} if frame_out is None else {"frame_out_truncated": frame_out}
+        np.savez_compressed(path, input=img, net_out=out, meta=np.array(c[1:5] + c[6:7]), **extra)
         print(path, out.shape, float(out.min()), float(out.max()), os.path.getsize(path))
 
 

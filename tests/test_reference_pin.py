@@ -10,7 +10,11 @@
     and the committed vectors re-derived (the fixtures are what the generator produces);
   * GPU:  the CUDA path (C ABI) against the reference-made vectors under the BASELINE gate.
 
-What this does not pin (no reference code restates it): `RealESRGANer` pre / tile / post-processing, `SRVGGNetCompact`.
+  * the frame path: the oracle's `enhance` against the reference's own pre- / post-processing around the network
+    (`_enhance_face` :516-542), which has upstream's conventions except that it truncates where upstream rounds.
+
+What this does not pin (no reference code restates it): upstream's final `round`, `pre_pad` / mod-pad, the tile loop, the
+gray / alpha / 16-bit branches, and `SRVGGNetCompact`.
 """
 import glob
 import os
@@ -89,7 +93,7 @@ def test_reference_module_live_equals_oracle_and_fixtures():
     mod = ref_pin.load_reference_module()
     for c in ref_pin.CASES:
         name, nb, cin = c[:3]
-        img, ref_out = ref_pin.run_case(mod, c)
+        img, ref_out, ref_frame = ref_pin.run_case(mod, c)
         model, _ = oracle.build_model(name)
         model.load_state_dict(make_synthetic_state_dict(name, 0), strict=True)
         with torch.no_grad():
@@ -98,6 +102,33 @@ def test_reference_module_live_equals_oracle_and_fixtures():
         z = np.load(os.path.join(ref_pin.OUT_DIR, ref_pin.case_name(c) + ".npz"))
         assert np.array_equal(z["input"], img)
         assert float(np.abs(z["net_out"] - ref_out).max()) <= 2e-5
+        if ref_frame is not None:                       # the reference's own frame path, live
+            assert np.array_equal(z["frame_out_truncated"], ref_frame)
+
+
+@pytest.mark.parametrize("path", [p for p in FIXTURES if "x2plus" not in p], ids=[i for i in IDS if "x2plus" not in i])
+def test_oracle_frame_path_against_the_reference_frame_path(path):
+    """Frame in -> frame out.  `frame_out_truncated` is what the reference's own pre- / post-processing around the
+    network produced (`AESRGANFaceRestorer._enhance_face`, aesrgan_face.py:516-542: BGR -> RGB, / 255, NCHW, model, HWC,
+    `np.clip(x * 255, 0, 255).astype(uint8)`, RGB -> BGR).  `RealESRGANer.enhance` has the same conventions but ROUNDS
+    where the reference truncates: the oracle's frame must be the reference's, or the reference's + 1 exactly where
+    the fraction of x * 255 is >= 0.5 -- which pins channel order, normalisation and layout on both sides of the net."""
+    from framewright_b200.archs import make_synthetic_state_dict
+    from oracle import oracle
+
+    name, nb, cin, img, net_out = _case(path)
+    ref_frame = np.load(path)["frame_out_truncated"]
+    ours, mode = oracle.make_upsampler(name, make_synthetic_state_dict(name, 0)).enhance(img)
+    assert mode == "RGB" and ours.shape == ref_frame.shape == (img.shape[0] * 4, img.shape[1] * 4, 3)
+    d = ours.astype(np.int16) - ref_frame.astype(np.int16)
+    assert d.min() >= 0 and d.max() <= 1
+    v = np.clip(net_out, 0.0, 1.0)[[2, 1, 0]].transpose(1, 2, 0).astype(np.float64) * 255.0     # BGR, HWC
+    frac = v - np.floor(v)
+    sure = np.abs(frac - 0.5) > 1e-3                    # away from the rounding boundary (fp32 summation order)
+    assert np.array_equal(d[sure] == 1, frac[sure] > 0.5)
+    assert 0.3 < float((d == 1).mean()) < 0.7           # about half the pixels round up: the relation is not vacuous
+    # a channel-order or layout slip on either side would break it: the same check with R and B swapped fails
+    assert (np.abs(ours[:, :, ::-1].astype(np.int16) - ref_frame.astype(np.int16)) > 1).mean() > 0.05
 
 
 def test_emulated_engine_rounding_passes_the_gate_on_the_reference_made_vectors():
