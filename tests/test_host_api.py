@@ -363,3 +363,27 @@ def test_dni_interpolates_state_dicts():
     from framewright_b200.engine import EngineError
     with pytest.raises(EngineError):
         RealESRGANer.dni(a, {"w": torch.ones(2, 3)}, [0.5, 0.5])
+
+
+def test_tile_size_helpers_keep_the_reference_rules(monkeypatch):
+    """The expectations of the reference's own tests for `calculate_optimal_tile_size` / `get_adaptive_tile_sequence`
+    (`/root/reference/tests/test_utils_gpu.py:126-207`), restated against `tile_sizing` (whose numbers come from the
+    engine's real footprint instead of the reference's cuDNN-era coefficients)."""
+    from framewright_b200 import tile_sizing as ts
+
+    monkeypatch.setattr(ts, "_free_vram_mb", lambda: 24000)
+    assert ts.calculate_optimal_tile_size(frame_resolution=(1920, 1080), scale_factor=4) == 0      # test_no_tiling_needed
+    monkeypatch.setattr(ts, "_free_vram_mb", lambda: 2000)
+    t = ts.calculate_optimal_tile_size(frame_resolution=(3840, 2160), scale_factor=4)              # test_tiling_needed_low_vram
+    assert t > 0 and t % 32 == 0
+    assert ts.calculate_optimal_tile_size((3840, 2160), 4, available_vram_mb=4000) > 0             # test_with_explicit_vram
+    assert ts.calculate_optimal_tile_size((7680, 4320), 4, available_vram_mb=1000) >= 128          # test_minimum_tile_size
+    seq = ts.get_adaptive_tile_sequence(frame_resolution=(1920, 1080), scale_factor=4, starting_tile_size=512)
+    assert all(a > b for a, b in zip(seq, seq[1:])) and all(x % 32 == 0 for x in seq)              # test_generate_sequence
+    assert 128 in ts.get_adaptive_tile_sequence((1920, 1080), 4, min_tile_size=128)                # test_minimum_in_sequence
+    # what is specific to this engine: the workspace a tile needs shrinks with the tile, and a B200 never tiles 720p
+    assert ts.engine_workspace_mb("RealESRGAN_x4plus", 1280, 720, tile=256) < ts.engine_workspace_mb("RealESRGAN_x4plus", 1280, 720)
+    assert ts.calculate_optimal_tile_size((1280, 720), 4, available_vram_mb=180000) == 0
+    # no device and nothing given: the reference's conservative 2048 MB default
+    monkeypatch.setattr(ts, "_free_vram_mb", lambda: None)
+    assert ts.calculate_optimal_tile_size((1920, 1080), 4) >= 128
