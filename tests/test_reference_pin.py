@@ -170,3 +170,29 @@ def test_gpu_against_reference_made_vector(native_lib, path):
     assert got.shape == want.shape
     assert rep["frac_within_1lsb"] >= oracle.GATE_FRAC_WITHIN_1LSB, rep
     assert rep["psnr_db"] >= oracle.GATE_PSNR_DB, rep
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/src/framewright/metrics.py"), reason="reference tree not mounted")
+def test_gate_metric_is_the_references_psnr():
+    """The gate's PSNR (`oracle.calculate_psnr`, used by `parity_report`) against the reference's own
+    `calculate_psnr` (`metrics.py:433-458`, the module loaded unmodified): same number on the same pair of images."""
+    import importlib.util
+    import sys
+
+    from oracle import oracle
+
+    spec = importlib.util.spec_from_file_location("_ref_metrics", "/root/reference/src/framewright/metrics.py")
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod
+    dont, sys.dont_write_bytecode = sys.dont_write_bytecode, True
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.dont_write_bytecode = dont
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (64, 80, 3), dtype=np.uint8)
+    for noise in (1, 2, 7, 40):
+        b = np.clip(a.astype(np.int16) + rng.integers(-noise, noise + 1, a.shape), 0, 255).astype(np.uint8)
+        assert abs(oracle.calculate_psnr(a, b) - mod.calculate_psnr(a, b)) < 1e-9
+        assert abs(oracle.parity_report(a, b)["psnr_db"] - mod.calculate_psnr(a, b)) < 1e-9
+    assert oracle.calculate_psnr(a, a) == mod.calculate_psnr(a, a) == float("inf")
