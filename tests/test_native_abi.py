@@ -64,10 +64,32 @@ def test_create_fails_loudly_without_gpu(native_lib):
 def test_plan_regions_matches_upstream_tile_process(native_lib, arch, scale, h, w, tile, tile_pad, pre_pad):
     """Region list == the upstream tile loop's slices (oracle/oracle.py::tile_process), including the final
     post_process crop of pre_pad / mod_pad."""
+    _check_region_plan(native_lib, arch, scale, h, w, tile, tile_pad, pre_pad)
+
+
+def test_plan_regions_random_shapes(native_lib):
+    """The same equality over 400 seeded random shapes: odd sizes (reflect mod-pad of the x2 network), tiles larger
+    and smaller than the frame, tile_pad from 0 up to more than a tile, pre_pad, frames one pixel over a tile boundary."""
+    rng = np.random.default_rng(2024)
+    for _ in range(400):
+        arch = int(rng.integers(0, 2))
+        scale = int(rng.choice([2, 4])) if arch == 0 else 4
+        h, w = int(rng.integers(8, 700)), int(rng.integers(8, 900))
+        tile = int(rng.choice([0, 24, 32, 48, 64, 100, 128, 200, 256, 400, 512]))
+        if rng.random() < 0.2 and tile:
+            h, w = tile * int(rng.integers(1, 4)) + int(rng.integers(-1, 2)), tile * int(rng.integers(1, 4)) + int(rng.integers(-1, 2))
+            h, w = max(h, 8), max(w, 8)
+        _check_region_plan(native_lib, arch, scale, h, w, tile, int(rng.choice([0, 1, 4, 10, 16, 40])),
+                           int(rng.choice([0, 0, 3, 10])))
+
+
+def _check_region_plan(native_lib, arch, scale, h, w, tile, tile_pad, pre_pad):
     import math
 
-    buf = (ctypes.c_int * (10 * 64))()
-    n = native_lib.b200sr_debug_plan_regions(arch, scale, h, w, tile, tile_pad, pre_pad, buf, 64)
+    cap = 4096
+    buf = (ctypes.c_int * (10 * cap))()
+    n = native_lib.b200sr_debug_plan_regions(arch, scale, h, w, tile, tile_pad, pre_pad, buf, cap)
+    assert 0 < n <= cap, (arch, scale, h, w, tile, tile_pad, pre_pad, n)
     got = [tuple(buf[i * 10:(i + 1) * 10]) for i in range(n)]
     mod = 2 if (arch == 0 and scale == 2) else 1
     Hp = -(-(h + pre_pad) // mod) * mod
@@ -88,7 +110,7 @@ def test_plan_regions_matches_upstream_tile_process(native_lib, arch, scale, h, 
                     continue
                 want.append((py0, px0, py1 - py0, px1 - px0, (y0 - py0) * scale, (x0 - px0) * scale, ch, cw,
                              y0 * scale, x0 * scale))
-    assert got == want
+    assert got == want, (arch, scale, h, w, tile, tile_pad, pre_pad)
     # the kept windows tile the destination frame exactly once
     cover = np.zeros((h * scale, w * scale), np.int32)
     for r in got:
@@ -133,6 +155,17 @@ def test_choose_th_bounds(native_lib):
         for (n, h, w) in [(1, 720, 1280), (4, 720, 1280), (1, 64, 64), (64, 480, 640), (1, 2880, 5120)]:
             th = native_lib.b200sr_debug_choose_th(coutp, n, h, w, 148)
             assert 1 <= th <= 512 // coutp
+
+
+def test_fused_rdb_work_list_random_shapes(native_lib):
+    """The same proof (coverage exactly once, dependencies produced by earlier items) over 40 seeded random shapes
+    around the strip / counter-block / column-tile boundaries."""
+    rng = np.random.default_rng(7)
+    for _ in range(40):
+        n = int(rng.integers(1, 4))
+        h = int(rng.choice([int(rng.integers(1, 200)), 8 * int(rng.integers(1, 20)) + int(rng.integers(-1, 2))]))
+        w = int(rng.choice([int(rng.integers(1, 600)), 128 * int(rng.integers(1, 5)) + int(rng.integers(-1, 2))]))
+        test_fused_rdb_work_list(native_lib, n, max(h, 1), max(w, 1))
 
 
 @pytest.mark.parametrize("n,h,w", [(1, 720, 1280), (2, 45, 300), (1, 16, 128), (1, 7, 50), (1, 333, 517)])
