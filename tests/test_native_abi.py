@@ -206,3 +206,58 @@ def test_fused_rdb_work_list(native_lib, n, h, w):
             assert dbase == (fn * 4 + dep) * nblk
             for r in range(max(y0 - 1, 0), min(y0 + rows + 1, h)):
                 assert 0 <= last_writer[fn, dep, r // fr] < i, (i, k, r)
+
+
+def test_plan_regions_equals_the_oracles_executable_tile_loop(native_lib):
+    """No restated loop in between: the oracle's own `pre_process` / `tile_process` / `post_process` run on a coordinate
+    image with a spy network that reports which slice it was given and stamps its output with (call index, local
+    row, local column).  From the stitched, cropped result one reads, per tile, the window that was kept and where it
+    came from -- exactly the ten numbers of a device-side region -- for 60 seeded random shapes."""
+    import framewright_b200  # noqa: F401
+    from oracle import oracle
+
+    class Spy(torch.nn.Module):
+        def __init__(self, s):
+            super().__init__()
+            self.s, self.calls = s, []
+
+        def forward(self, t):
+            _, _, th, tw = t.shape
+            self.calls.append((int(t[0, 0, 0, 0]), int(t[0, 1, 0, 0]), th, tw))
+            s = self.s
+            out = torch.empty(1, 3, th * s, tw * s)
+            out[0, 0] = float(len(self.calls) - 1)
+            out[0, 1] = torch.arange(th * s, dtype=torch.float32)[:, None]
+            out[0, 2] = torch.arange(tw * s, dtype=torch.float32)[None, :]
+            return out
+
+    rng = np.random.default_rng(99)
+    for _ in range(60):
+        scale = int(rng.choice([2, 4]))
+        h, w = int(rng.integers(8, 300)), int(rng.integers(8, 300))
+        tile = int(rng.choice([16, 24, 32, 50, 64, 128, 256]))
+        tile_pad, pre_pad = int(rng.choice([0, 2, 10, 20])), int(rng.choice([0, 0, 3, 10]))
+        spy = Spy(scale)
+        up = oracle.RealESRGANer(scale=scale, model=spy, tile=tile, tile_pad=tile_pad, pre_pad=pre_pad)
+        up.pre_process(np.zeros((h, w, 3), np.float32))
+        _, _, Hp, Wp = up.img.shape
+        up.img = torch.stack([torch.arange(Hp, dtype=torch.float32)[:, None].expand(Hp, Wp),
+                              torch.arange(Wp, dtype=torch.float32)[None, :].expand(Hp, Wp),
+                              torch.zeros(Hp, Wp)])[None]
+        up.tile_process()
+        out = up.post_process()[0].numpy()
+        assert out.shape == (3, h * scale, w * scale)
+        want = []
+        for r, (py0, px0, th, tw) in enumerate(spy.calls):
+            ys, xs = np.nonzero(out[0] == r)
+            if ys.size == 0:
+                continue                                   # a tile that lies entirely in the cropped padding
+            dy0, dx0, ch, cw = ys.min(), xs.min(), ys.max() - ys.min() + 1, xs.max() - xs.min() + 1
+            assert ys.size == ch * cw                      # the kept window is a full rectangle
+            want.append((py0, px0, th, tw, int(out[1, dy0, dx0]), int(out[2, dy0, dx0]), int(ch), int(cw),
+                         int(dy0), int(dx0)))
+        cap = 4096
+        buf = (ctypes.c_int * (10 * cap))()
+        n = native_lib.b200sr_debug_plan_regions(0, scale, h, w, tile, tile_pad, pre_pad, buf, cap)
+        got = [tuple(buf[i * 10:(i + 1) * 10]) for i in range(n)]
+        assert got == want, (scale, h, w, tile, tile_pad, pre_pad)
