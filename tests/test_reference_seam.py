@@ -721,3 +721,100 @@ def test_video_restorer_thread_parallel_caller_runs_verbatim_against_the_mirror(
         want = oracle.make_upsampler(name, sd, tile=t, tile_pad=10, pre_pad=0).enhance(img)[0]
         assert np.array_equal(cv2.imread(str(outd / frames[i].name), cv2.IMREAD_UNCHANGED), want), (i, t)
     mine.clear_upsampler_cache()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_the_documented_enhance_frames_patch_applies_and_runs(tmp_path, monkeypatch):
+    """SURVEY 8 f2, the binding a maintainer would add: the `+` lines of INTEGRATION.md's `enhance_frames` diff are taken
+    from that file, inserted into the reference's `VideoRestorer.enhance_frames` source (restorer.py:1604-1705) at the
+    documented place, and the patched method runs -- frames directory in, `enhanced_dir` out through the sharded
+    scheduler (two worker processes, stand-in engine), the reference's own `CheckpointManager` fed per frame,
+    `_update_progress` per frame, resume skipping what the checkpoint holds."""
+    import functools
+    import types
+
+    import cv2
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from sched_helpers import fake_engine
+    from test_adapters import _checkpoint_module
+
+    import framewright_b200  # noqa: F401
+    from framewright_b200 import multi_gpu as mg
+    from framewright_b200 import pytorch_realesrgan as mine
+    from framewright_b200 import restorer_adapter as ra
+    from framewright_b200.tile_sizing import get_adaptive_tile_sequence
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = doc[doc.index("--- a/src/framewright/restorer.py   (enhance_frames"):]
+    block = block[:block.index("```")]
+    plus = [ln[3:] for ln in block.splitlines() if ln.startswith("  +")]          # "  +<code>" -> "<code>"
+    assert len(plus) >= 10 and plus[0].strip().startswith("if self._get_enhancement_backend()")
+    src = _reference_method(os.path.join(REF, "restorer.py"), "VideoRestorer", "enhance_frames").splitlines()
+    at = next(i for i, ln in enumerate(src) if 'logger.info(f"Enhancing {total_frames} frames using' in ln)
+    indent_ref = len(src[at]) - len(src[at].lstrip())
+    indent_doc = len(plus[0]) - len(plus[0].lstrip())
+    patched = src[:at + 1] + [" " * indent_ref + ln[indent_doc:] for ln in plus] + src[at + 1:]
+
+    class Report:
+        def __init__(self, total_operations=0):
+            self.total, self.ok, self.errors = total_operations, 0, []
+
+        def add_success(self):
+            self.ok += 1
+
+        def add_error(self, name, exc):
+            self.errors.append(name)
+
+        def summary(self):
+            return f"{self.ok} ok"
+
+    quiet = types.SimpleNamespace(info=lambda *a, **k: None, warning=lambda *a, **k: None, error=lambda *a, **k: None,
+                                  debug=lambda *a, **k: None)
+    ns = {"logger": quiet, "EnhancementError": ra.EnhancementError, "ErrorReport": Report,
+          "get_adaptive_tile_sequence": get_adaptive_tile_sequence, "PyTorchESRGANConfig": mine.PyTorchESRGANConfig,
+          "convert_ncnn_model_name": mine.convert_ncnn_model_name}
+    exec("\n".join(patched), ns)
+
+    d = mg.MultiGPUDistributor(gpus=[mg.GPUInfo(0, "GPU0", 1, 1, 0.0), mg.GPUInfo(1, "GPU1", 1, 1, 0.0)],
+                               strategy=mg.LoadBalanceStrategy.ROUND_ROBIN, workers_per_gpu=1,
+                               model_name="RealESRGAN_x2plus", scale=2)
+    # (no GPU here: the adapter the patch imports is given the CPU pool and the stand-in engine; nothing else differs)
+    monkeypatch.setattr(ra, "enhance_frames_batched",
+                        functools.partial(ra.enhance_frames_batched, distributor=d, engine_factory=fake_engine))
+    try:
+        frames_dir, enhanced = tmp_path / "frames", tmp_path / "enhanced"
+        frames_dir.mkdir()
+        for i in range(9):
+            cv2.imwrite(str(frames_dir / f"frame_{i + 1:08d}.png"), np.full((6, 8, 3), 11 * i, np.uint8))
+        ck = _checkpoint_module()
+        cm = ck.CheckpointManager(tmp_path, checkpoint_interval=2)
+        cm.create_checkpoint(stage="extract", total_frames=9, source_path="clip.mp4")
+        progress = []
+        me = types.SimpleNamespace(
+            _dedup_result=None, checkpoint_manager=cm, metadata={"width": 8, "height": 6},
+            config=types.SimpleNamespace(frames_dir=frames_dir, enhanced_dir=enhanced, unique_frames_dir=tmp_path / "u",
+                                         model_name="realesrgan-x2plus", scale_factor=2, gpu_id=None,
+                                         continue_on_error=False, parallel_frames=1),
+            _get_enhancement_backend=lambda: "pytorch", _get_tile_size=lambda: 0,
+            _update_progress=lambda **k: progress.append(k))
+        assert ns["enhance_frames"](me) == 9
+        assert sorted(p.name for p in enhanced.glob("*.png")) == [f"frame_{i + 1:08d}.png" for i in range(9)]
+        got = cv2.imread(str(enhanced / "frame_00000004.png"), cv2.IMREAD_UNCHANGED)
+        assert got.shape == (12, 16, 3) and int(got[0, 0, 0]) == 33
+        loaded = cm.load_checkpoint()
+        assert loaded.stage == "enhance" and sorted(f.frame_number for f in loaded.frames if f.processed) == list(range(1, 10))
+        done = [p["frames_completed"] for p in progress if "eta_seconds" not in p]
+        assert done[0] == 0 and sorted(done[1:]) == list(range(1, 10)) and progress[-1]["progress"] == 1.0
+        assert me._error_report.ok == 9 and not me._error_report.errors
+        # a second run resumes: the checkpoint holds every frame, nothing is enhanced again
+        progress.clear()
+        assert ns["enhance_frames"](me) == 9 and not progress
+        # the ncnn backend is untouched by the patch: the reference's own path continues below it
+        me._get_enhancement_backend = lambda: "ncnn"
+        me._enhance_frames_sequential = lambda frames, tile, seq, rep: 0
+        me.checkpoint_manager = None
+        assert ns["enhance_frames"](me) == 9       # (its final count is the directory listing)
+    finally:
+        d.close()
