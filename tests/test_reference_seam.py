@@ -668,7 +668,8 @@ def test_video_restorer_thread_parallel_caller_runs_verbatim_against_the_mirror(
           "EnhancementError": EnhancementError, "is_pytorch_esrgan_available": mine.is_pytorch_esrgan_available,
           "convert_ncnn_model_name": mine.convert_ncnn_model_name, "PyTorchESRGANConfig": mine.PyTorchESRGANConfig,
           "enhance_frame_pytorch": mine.enhance_frame_pytorch, "validate_frame_integrity": validate_frame_integrity}
-    for meth in ("_enhance_frames_parallel", "_enhance_single_frame", "_enhance_single_frame_pytorch"):
+    for meth in ("_enhance_frames_parallel", "_enhance_frames_sequential", "_enhance_single_frame",
+                 "_enhance_single_frame_pytorch"):
         exec(_reference_method(os.path.join(REF, "restorer.py"), "VideoRestorer", meth), ns)
 
     ind, outd = tmp_path / "frames", tmp_path / "enhanced"
@@ -700,6 +701,22 @@ def test_video_restorer_thread_parallel_caller_runs_verbatim_against_the_mirror(
     want_up = oracle.make_upsampler(name, make_synthetic_state_dict(name, 0), tile=0, pre_pad=0)
     for i, img in enumerate(imgs):
         assert np.array_equal(cv2.imread(str(outd / frames[i].name), cv2.IMREAD_UNCHANGED), want_up.enhance(img)[0])
+
+    # the sequential caller (:1707-1821, parallel_frames = 1), the same three frames; then with a device on which only
+    # tiles <= 24 fit: its ladder (one step per failure, no race) ends on 24 and the failed frame is retried there
+    shutil.rmtree(outd)
+    outd.mkdir()
+    checkpointed.clear()
+    rep = Report()
+    assert ns["_enhance_frames_sequential"](me, frames[:3], 0, [32, 24, 16], rep) == 3 and rep.ok == 3
+    assert sorted(checkpointed) == [1, 2, 3]
+    assert np.array_equal(cv2.imread(str(outd / frames[1].name), cv2.IMREAD_UNCHANGED), want_up.enhance(imgs[1])[0])
+    state.update(oom_above_tile=24, tiles=[])
+    mine.clear_upsampler_cache()
+    rep = Report()
+    assert ns["_enhance_frames_sequential"](me, frames[:3], 48, [48, 32, 24, 16], rep) == 3 and rep.ok == 3
+    assert {t for t, _ in state["tiles"]} == {24}
+    state.update(oom_above_tile=None, tiles=[])
 
     # the device "fills up": nothing above a 24-pixel tile fits any more.  The caller starts from its configured tile
     # and every failing thread steps the shared tile size down once (the reference's own logic, racy by design: the
