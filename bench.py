@@ -466,6 +466,23 @@ def run_b200(args):
                           "pass": bool(rep["frac_within_1lsb"] >= oracle.GATE_FRAC_WITHIN_1LSB
                                        and rep["psnr_db"] >= oracle.GATE_PSNR_DB),
                           "what": "frame 0 of the timed device-resident output vs the fp32 CPU oracle (5120x2880x3)"}
+        try:
+            # the CUDA path against a vector made by the REFERENCE'S OWN RRDB code (oracle/ref_pin.py; committed fixture)
+            from framewright_b200.archs import make_synthetic_state_dict
+            from framewright_b200.engine import B200Engine
+            from oracle import ref_pin
+
+            z = np.load(os.path.join(ROOT, "tests", "golden", "reference_made", "RealESRGAN_x4plus_24x28_mixed31.npz"))
+            e2 = B200Engine(MODEL, make_synthetic_state_dict(MODEL, 0), gpu_id=local_rank)
+            got = e2.upscale_host(np.ascontiguousarray(z["input"]))
+            e2.close()
+            r2 = oracle.parity_report(ref_pin.quantise(z["net_out"]), got)
+            line["parity"]["reference_made_vector"] = {
+                "frac_within_1lsb": r2["frac_within_1lsb"], "psnr_db": r2["psnr_db"], "max_abs": r2["max_abs"],
+                "what": "CUDA path vs the output of the reference's in-tree ESRGAN generator (aesrgan_face.py:171-268) "
+                        "on the same weights, 24x28 frame, quantised per upstream's post-process"}
+        except Exception as e:   # never at the cost of the line
+            line["parity"]["reference_made_vector"] = {"error": f"{type(e).__name__}: {e}"}
         line["cpu_baseline"] = {"value": 1.0 / cdt, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"one full 1280x720 frame (frame 0 of the timed batch), one pass of the fp32 "
                                           f"torch oracle: {cdt:.1f} s; no extrapolation"}
